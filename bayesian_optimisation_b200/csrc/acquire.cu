@@ -1,0 +1,423 @@
+// K4: fused acquisition sweep                        point_selector.py:81,90-98,204-207
+//
+// For a chunk of S candidates (a "super-tile"):
+//   1. panel_kernel   k_*[j, c] = exp(-0.5 sum_k (x_jk - p_ck)^2 / ell_k^2), written once, in
+//                     DMMA-fragment order, plus the partial posterior means alpha . k_*;
+//                     explicit candidate blocks are staged with a bulk-TMA copy.
+//   2. trigemm_kernel V = W k_* on the FP64 tensor path (W = L^-1 lower triangular, packed),
+//                     operands streamed by bulk-TMA copies through a 5-stage mbarrier ring,
+//                     fused epilogue: column sums of V^2 (never stores V).
+//   3. finalize_kernel sigma^2 = prior - |V_c|^2, mu, LCB / EI, warp-level arg-max with the
+//                     reference's tie rule (largest score, then smallest flat index).
+//   4. merge_kernel   folds the block winners into the running (score, index) of the sweep.
+//
+// Every reduction has a fixed order that depends only on n_pad, so a candidate's score is
+// bit-identical no matter which chunk, CTA or GPU scored it.
+#include "common.cuh"
+#include "fit.cuh"
+
+namespace bogp {
+
+struct CandDesc {
+    const double* points;     // explicit: c_total x dim
+    const double* axes;       // grid: concatenated axes
+    int           len[BOGP_MAX_DIM];
+    int           off[BOGP_MAX_DIM];
+    int64_t       c_total;
+    double        cross_jitter;
+};
+
+struct PanelArgs {
+    CandDesc cand;
+    const double* x_pad; const double* inv_ell2; const double* alpha;
+    double* panel; double* mupart;
+    int64_t c0, c_end;    // chunk start (global flat index), end of the requested range
+    int64_t S;            // chunk capacity (stride of mupart)
+    int n, n_pad, dim;
+};
+
+// grid (ceil(cur/64), n_pad/256), 256 threads: warp w <-> candidates 8w..8w+7 of the tile,
+// lane = (cand % 8) * 4 + (j % 4): exactly the B-fragment order of DMMA.8x8x4, so each warp
+// store is one contiguous 256-byte line of the packed panel.
+__global__ void __launch_bounds__(256) panel_kernel(PanelArgs p) {
+    __shared__ __align__(128) double ps_raw[kAcqBN * BOGP_MAX_DIM];   // candidate block, [cand][dim] as in HBM
+    __shared__ double xs[BOGP_MAX_DIM][kAcqBM + 1];
+    __shared__ double al[kAcqBM];
+    __shared__ double sl[BOGP_MAX_DIM];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ct = blockIdx.x, jb = blockIdx.y;
+    const int64_t cbase = p.c0 + (int64_t)ct * kAcqBN;
+    const int dim = p.dim;
+
+    const bool explicit_mode = p.cand.points != nullptr;
+    // number of valid candidates in this tile (>= 1 by construction of the grid)
+    const int64_t remain = p.c_end - cbase;
+    const int nvalid = remain >= kAcqBN ? kAcqBN : (int)remain;
+    bool used_tma = false;
+    if (explicit_mode) {
+        const double* src = p.cand.points + cbase * dim;
+        const uint32_t bytes = (uint32_t)nvalid * dim * 8;
+        // bulk-TMA staging of the candidate block (16-byte granularity and alignment required)
+        if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            used_tma = true;
+            if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+            __syncthreads();
+            if (tid == 0) { mbar_expect_tx(&bar, bytes); bulk_g2s(ps_raw, src, bytes, &bar); }
+        }
+    }
+    // measured points of this row block, transposed; alpha; 1/ell^2
+    for (int i = tid; i < kAcqBM * dim; i += 256) {
+        int r = i / dim, k = i % dim;
+        xs[k][r] = p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k];
+    }
+    al[tid] = p.alpha[jb * kAcqBM + tid];
+    if (tid < dim) sl[tid] = p.inv_ell2[tid];
+
+    if (explicit_mode) {
+        if (used_tma) {
+            mbar_wait(&bar, 0);
+        } else {
+            for (int i = tid; i < nvalid * dim; i += 256) ps_raw[i] = p.cand.points[cbase * dim + i];
+        }
+    } else if (tid < nvalid) {
+        int64_t f = cbase + tid;     // mixed-radix digits of the flat index, axis 0 slowest (select_parameters.py:273-279)
+        for (int k = dim - 1; k >= 0; k--) {
+            const int64_t q = f / p.cand.len[k];
+            const int dgt = (int)(f - q * p.cand.len[k]);
+            ps_raw[tid * dim + k] = p.cand.axes[p.cand.off[k] + dgt];
+            f = q;
+        }
+    }
+    __syncthreads();
+
+    const int nl = warp * 8 + (lane >> 2), jj = lane & 3;
+    const int64_t cglob = cbase + nl;
+    const int ncl = nl < nvalid ? nl : nvalid - 1;     // tail tiles recompute the last valid candidate; masked later
+    double pc[BOGP_MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < BOGP_MAX_DIM; k++) pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0;
+
+    double* tile0 = p.panel + ((int64_t)ct * (p.n_pad / kAcqKB) + (int64_t)jb * (kAcqBM / kAcqKB)) * (kAcqKB * kAcqBN);
+    double mu = 0.0;
+    for (int t = 0; t < kAcqBM / 4; t++) {
+        const int jl = t * 4 + jj;
+        const int j = jb * kAcqBM + jl;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < BOGP_MAX_DIM; k++) {
+            if (k < dim) { const double df = pc[k] - xs[k][jl]; s += (df * df) * sl[k]; }
+        }
+        double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
+        if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
+        mu += al[jl] * v;
+        // tile kt = jb*16 + t/4, kk = t%4, n8 = warp
+        tile0[(int64_t)(t >> 2) * (kAcqKB * kAcqBN) + ((t & 3) * 8 + warp) * 32 + lane] = v;
+    }
+    mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+    mu += __shfl_xor_sync(0xffffffffu, mu, 2);
+    if (jj == 0) p.mupart[(int64_t)jb * p.S + (int64_t)ct * kAcqBN + nl] = mu;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TriArgs {
+    const double* wp; const double* panel; double* qpart;
+    int nI, nct, n_pad; int64_t S;
+};
+
+constexpr int kATileBytes = kAcqBM * kAcqKB * 8;   // 32 KB
+constexpr int kBTileBytes = kAcqKB * kAcqBN * 8;   //  8 KB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;
+constexpr size_t kTriSmem = (size_t)kAcqStages * kStageBytes + 2 * kAcqStages * 8 + 4 * kAcqBN * 8 + 64;
+
+// CTA = (row block ib of W, candidate tile ct); 8 consumer warps (4 x 2, warp tile 64 x 32)
+// + 1 producer warp issuing bulk-TMA copies.  Heaviest row blocks are scheduled first.
+__global__ void __launch_bounds__(288, 1) trigemm_kernel(TriArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double*   sA   = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kAcqStages * kStageBytes);
+    uint64_t* empt = full + kAcqStages;
+    double*   red  = reinterpret_cast<double*>(empt + kAcqStages);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ib = g.nI - 1 - (int)(blockIdx.x / g.nct);
+    const int ct = (int)(blockIdx.x % g.nct);
+    const int nk = (ib + 1) * (kAcqBM / kAcqKB);
+
+    if (tid == 0) {
+        for (int s = 0; s < kAcqStages; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 8); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const double* wsrc = g.wp + (int64_t)ib * (ib + 1) / 2 * (kAcqBM / kAcqKB) * (kAcqBM * kAcqKB);
+            const double* psrc = g.panel + (int64_t)ct * (g.n_pad / kAcqKB) * (kAcqKB * kAcqBN);
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % kAcqStages;
+                if (kt >= kAcqStages) mbar_wait(&empt[s], ((kt / kAcqStages) - 1) & 1);
+                unsigned char* dst = smem_raw + (size_t)s * kStageBytes;
+                mbar_expect_tx(&full[s], kStageBytes);
+                bulk_g2s(dst, wsrc + (int64_t)kt * (kAcqBM * kAcqKB), kATileBytes, &full[s]);
+                bulk_g2s(dst + kATileBytes, psrc + (int64_t)kt * (kAcqKB * kAcqBN), kBTileBytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < nk; kt++) {
+        const int s = kt % kAcqStages;
+        mbar_wait(&full[s], (kt / kAcqStages) & 1);
+        const double* a = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
+        const double* b = a + kAcqBM * kAcqKB;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) af[i] = a[((kk * 32 + wm * 8 + i) << 5) + lane];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[j] = b[((kk * 8 + wn * 4 + j) << 5) + lane];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empt[s]);
+    }
+
+    // fused epilogue: column sums of squares over the 256 rows of this block
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s += acc[i][j][e] * acc[i][j][e];
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            if (lane < 4) red[wm * kAcqBN + wn * 32 + j * 8 + 2 * lane + e] = s;
+        }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid < kAcqBN) {
+        const double q = ((red[tid] + red[kAcqBN + tid]) + red[2 * kAcqBN + tid]) + red[3 * kAcqBN + tid];
+        g.qpart[(int64_t)ib * g.S + (int64_t)ct * kAcqBN + tid] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct FinalArgs {
+    const double* qpart; const double* mupart;
+    double* mu_out; double* sigma_out; double* acq_out;   // already offset to this chunk (or null)
+    double* block_score; long long* block_index; int* nan_flag;
+    int64_t c0, cur, S; int nI; int kind; double explore, f_best, prior;
+};
+
+__device__ __forceinline__ double acquisition_value(int kind, double mu, double sigma, double explore, double f_best) {
+    if (kind == BOGP_ACQ_LCB) return __dsub_rn(__dmul_rn(explore, sigma), mu);   // two roundings like numpy, no FMA
+    const double imp = f_best - mu;
+    if (!(sigma > 0.0)) return imp > 0.0 ? imp : 0.0;
+    const double z = imp / sigma;
+    return imp * normcdf(z) + sigma * (exp(-0.5 * z * z) * 0.3989422804014326779);
+}
+
+__device__ __forceinline__ void block_argmax(double s, long long i, double* block_score, long long* block_index, int slot) {
+    __shared__ double ws[8]; __shared__ long long wi[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, s, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (better(os, oi, s, i)) { s = os; i = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ws[warp] = s; wi[warp] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (better(ws[w], wi[w], s, i)) { s = ws[w]; i = wi[w]; }
+        block_score[slot] = s; block_index[slot] = i;
+    }
+}
+
+constexpr long long kNoIndex = 0x7fffffffffffffffLL;
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalArgs f) {
+    const int64_t cl = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double score = -INFINITY; long long idx = kNoIndex;
+    if (cl < f.cur) {
+        double q = 0.0, mu = 0.0;
+        for (int b = 0; b < f.nI; b++) { q += f.qpart[(int64_t)b * f.S + cl]; mu += f.mupart[(int64_t)b * f.S + cl]; }
+        const double var = f.prior - q;
+        const double sigma = sqrt(fabs(var));                   // np.sqrt(np.abs(.)), point_selector.py:98
+        score = acquisition_value(f.kind, mu, sigma, f.explore, f.f_best);
+        idx = f.c0 + cl;
+        if (f.mu_out) f.mu_out[cl] = mu;
+        if (f.sigma_out) f.sigma_out[cl] = sigma;
+        if (f.acq_out) f.acq_out[cl] = score;
+        if (score != score) { atomicExch(f.nan_flag, 1); score = -INFINITY; }
+    }
+    block_argmax(score, idx, f.block_score, f.block_index, blockIdx.x);
+}
+
+// acquisition + arg-max on mu/sigma already on the device (lower_confidence_bound, :197-207)
+__global__ void __launch_bounds__(256) score_kernel(const double* __restrict__ mu, const double* __restrict__ sigma, int64_t c,
+                                                    int kind, double explore, double f_best, double* acq_out,
+                                                    double* block_score, long long* block_index, int* nan_flag) {
+    double best = -INFINITY; long long bi = kNoIndex;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < c; i += (int64_t)gridDim.x * 256) {
+        double s = acquisition_value(kind, mu[i], sigma[i], explore, f_best);
+        if (acq_out) acq_out[i] = s;
+        if (s != s) { atomicExch(nan_flag, 1); continue; }
+        if (better(s, i, best, bi)) { best = s; bi = i; }
+    }
+    block_argmax(best, bi, block_score, block_index, blockIdx.x);
+}
+
+// best[0] (score), besti[0] (index): running winner, folded with nblocks block winners.
+__global__ void __launch_bounds__(256) merge_kernel(const double* block_score, const long long* block_index, int nblocks,
+                                                    double* best, long long* besti) {
+    __shared__ double ws[8]; __shared__ long long wi[8];
+    double s = -INFINITY; long long i = kNoIndex;
+    for (int b = threadIdx.x; b < nblocks; b += 256) if (better(block_score[b], block_index[b], s, i)) { s = block_score[b]; i = block_index[b]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, s, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (better(os, oi, s, i)) { s = os; i = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; wi[threadIdx.x >> 5] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) if (better(ws[w], wi[w], s, i)) { s = ws[w]; i = wi[w]; }
+        if (better(s, i, best[0], besti[0])) { best[0] = s; besti[0] = i; }
+    }
+}
+
+__global__ void init_best_kernel(double* best, long long* besti, int* nan_flag) {
+    best[0] = -INFINITY; besti[0] = kNoIndex; nan_flag[0] = 0;
+}
+
+struct AcqLayout { size_t panel, qpart, mupart, axes_unused, total; int64_t S; };
+static AcqLayout acq_layout(int64_t n_pad, int64_t max_chunk) {
+    AcqLayout l{}; size_t off = 0;
+    int64_t S = (max_chunk + kAcqBN - 1) / kAcqBN * kAcqBN;
+    if (S < kAcqBN) S = kAcqBN;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    const int64_t nI = n_pad / kAcqBM;
+    l.panel = take((size_t)n_pad * S * 8); l.qpart = take((size_t)nI * S * 8); l.mupart = take((size_t)nI * S * 8);
+    l.total = off; l.S = S;
+    return l;
+}
+
+}  // namespace bogp
+
+using namespace bogp;
+
+extern "C" size_t bogp_acquire_workspace_bytes(const bogp_fit* fit, int64_t max_chunk) {
+    if (!fit || max_chunk <= 0) return 0;
+    return acq_layout(bogp_fit_n_pad(fit), max_chunk).total;
+}
+
+extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand, int64_t c_begin, int64_t c_end,
+                            int kind, double explore, double f_best, double prior_diag, double* d_mu_out,
+                            double* d_sigma_out, double* d_acq_out, void* d_workspace, size_t workspace_bytes,
+                            double* h_best_score, int64_t* h_best_index) {
+    if (!ctx || !fit || !cand || !d_workspace || c_begin < 0 || c_end <= c_begin || c_end > cand->c_total ||
+        (kind != BOGP_ACQ_LCB && kind != BOGP_ACQ_EI)) {
+        set_error("bogp_acquire: bad argument"); return BOGP_ERR_BAD_ARG;
+    }
+    const int dim = fit_dim(fit);
+    const int64_t n_pad = bogp_fit_n_pad(fit);
+    const int nI = (int)(n_pad / kAcqBM);
+    CandDesc cd{};
+    cd.points = cand->d_points; cd.axes = cand->d_axes; cd.c_total = cand->c_total; cd.cross_jitter = cand->cross_jitter;
+    if (!cd.points) {
+        if (!cd.axes || !cand->h_axis_len) { set_error("bogp_acquire: neither points nor grid axes given"); return BOGP_ERR_BAD_ARG; }
+        int64_t prod = 1; int off = 0;
+        for (int k = 0; k < dim; k++) {
+            cd.len[k] = cand->h_axis_len[k]; cd.off[k] = off; off += cd.len[k];
+            if (cd.len[k] <= 0) { set_error("bogp_acquire: empty grid axis %d", k); return BOGP_ERR_BAD_ARG; }
+            prod *= cd.len[k];
+        }
+        if (prod != cand->c_total) { set_error("bogp_acquire: grid has %lld points, c_total says %lld", (long long)prod, (long long)cand->c_total); return BOGP_ERR_BAD_ARG; }
+    }
+    // chunk capacity from the workspace size
+    const size_t per_cand = (size_t)(n_pad + 2 * nI) * 8;
+    int64_t S = (int64_t)(workspace_bytes / per_cand) / kAcqBN * kAcqBN;
+    if (S < kAcqBN) { set_error("bogp_acquire: workspace too small"); return BOGP_ERR_WORKSPACE; }
+    if (S > (int64_t)kMaxReduceBlocks * 256) S = (int64_t)kMaxReduceBlocks * 256;
+    if (S > c_end - c_begin) S = (c_end - c_begin + kAcqBN - 1) / kAcqBN * kAcqBN;
+    const AcqLayout l = acq_layout(n_pad, S);
+    if (l.total > workspace_bytes) { set_error("bogp_acquire: workspace too small"); return BOGP_ERR_WORKSPACE; }
+    char* base = static_cast<char*>(d_workspace);
+    double* panel = (double*)(base + l.panel); double* qpart = (double*)(base + l.qpart); double* mupart = (double*)(base + l.mupart);
+
+    static bool configured = false;
+    if (!configured) {
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmem));
+        configured = true;
+    }
+    cudaStream_t st = ctx->stream;
+    double* best = ctx->d_scalars; long long* besti = reinterpret_cast<long long*>(ctx->d_scalars + 1);
+    int* nan_flag = ctx->d_flags;
+    init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
+
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += S) {
+        const int64_t cur = (c_end - c0 < S) ? (c_end - c0) : S;
+        const int nct = (int)((cur + kAcqBN - 1) / kAcqBN);
+        PanelArgs pa{cd, fit_xpad(fit), fit_inv_ell2(fit), fit_alpha(fit), panel, mupart, c0, c_end, S, (int)fit_n(fit), (int)n_pad, dim};
+        panel_kernel<<<dim3(nct, nI), 256, 0, st>>>(pa); BOGP_LAUNCH_CHECK(ctx);
+        TriArgs ta{fit_wp(fit), panel, qpart, nI, nct, (int)n_pad, S};
+        trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta); BOGP_LAUNCH_CHECK(ctx);
+        const int nfb = (int)((cur + 255) / 256);
+        if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }
+        const int64_t o = c0 - c_begin;
+        FinalArgs fa{qpart, mupart, d_mu_out ? d_mu_out + o : nullptr, d_sigma_out ? d_sigma_out + o : nullptr,
+                     d_acq_out ? d_acq_out + o : nullptr, ctx->d_block_score, ctx->d_block_index, nan_flag,
+                     c0, cur, S, nI, kind, explore, f_best, prior_diag};
+        finalize_kernel<<<nfb, 256, 0, st>>>(fa); BOGP_LAUNCH_CHECK(ctx);
+        merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti); BOGP_LAUNCH_CHECK(ctx);
+    }
+    if (h_best_score || h_best_index) {
+        double hs; long long hi; int hn;
+        BOGP_CUDA_CHECK(cudaMemcpyAsync(&hs, best, 8, cudaMemcpyDeviceToHost, st));
+        BOGP_CUDA_CHECK(cudaMemcpyAsync(&hi, besti, 8, cudaMemcpyDeviceToHost, st));
+        BOGP_CUDA_CHECK(cudaMemcpyAsync(&hn, nan_flag, 4, cudaMemcpyDeviceToHost, st));
+        BOGP_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (hn) { set_error("bogp_acquire: NaN acquisition value (reference raises IndexError, point_selector.py:207)"); return BOGP_ERR_NAN_SCORE; }
+        if (h_best_score) *h_best_score = hs;
+        if (h_best_index) *h_best_index = (int64_t)hi;
+    }
+    return BOGP_OK;
+}
+
+extern "C" int bogp_score_argmax(bogp_ctx* ctx, const double* d_mu, const double* d_sigma, int64_t c, int kind, double explore,
+                                 double f_best, double* d_acq_out, double* h_best_score, int64_t* h_best_index) {
+    if (!ctx || !d_mu || !d_sigma || c <= 0 || (kind != BOGP_ACQ_LCB && kind != BOGP_ACQ_EI)) { set_error("bogp_score_argmax: bad argument"); return BOGP_ERR_BAD_ARG; }
+    cudaStream_t st = ctx->stream;
+    double* best = ctx->d_scalars; long long* besti = reinterpret_cast<long long*>(ctx->d_scalars + 1);
+    int* nan_flag = ctx->d_flags;
+    init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
+    int nb = (int)((c + 255) / 256); if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
+    score_kernel<<<nb, 256, 0, st>>>(d_mu, d_sigma, c, kind, explore, f_best, d_acq_out, ctx->d_block_score, ctx->d_block_index, nan_flag); BOGP_LAUNCH_CHECK(ctx);
+    merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nb, best, besti); BOGP_LAUNCH_CHECK(ctx);
+    double hs; long long hi; int hn;
+    BOGP_CUDA_CHECK(cudaMemcpyAsync(&hs, best, 8, cudaMemcpyDeviceToHost, st));
+    BOGP_CUDA_CHECK(cudaMemcpyAsync(&hi, besti, 8, cudaMemcpyDeviceToHost, st));
+    BOGP_CUDA_CHECK(cudaMemcpyAsync(&hn, nan_flag, 4, cudaMemcpyDeviceToHost, st));
+    BOGP_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (hn) { set_error("bogp_score_argmax: NaN acquisition value (reference raises IndexError, point_selector.py:207)"); return BOGP_ERR_NAN_SCORE; }
+    if (h_best_score) *h_best_score = hs;
+    if (h_best_index) *h_best_index = (int64_t)hi;
+    return BOGP_OK;
+}

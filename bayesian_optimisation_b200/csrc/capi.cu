@@ -1,0 +1,60 @@
+// Context management and error reporting of libbogp.
+#include "common.cuh"
+#include <cstring>
+
+namespace bogp {
+static thread_local char g_error[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+}  // namespace bogp
+
+using namespace bogp;
+
+extern "C" const char* bogp_version(void) { return "bogp 1 sm_100a"; }
+extern "C" const char* bogp_last_error(void) { return g_error; }
+
+extern "C" int bogp_create(int device, bogp_ctx** out) {
+    if (!out) { set_error("bogp_create: null output pointer"); return BOGP_ERR_BAD_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("bogp_create: no CUDA device available (%s); libbogp has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return BOGP_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("bogp_create: device %d out of range [0,%d)", device, count); return BOGP_ERR_BAD_ARG; }
+    BOGP_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BOGP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("bogp_create: device %d is sm_%d%d; libbogp is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return BOGP_ERR_CUDA;
+    }
+    bogp_ctx* c = new bogp_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device; c->sm_count = prop.multiProcessorCount; c->stream = nullptr; c->launches = 0;
+    BOGP_CUDA_CHECK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
+    BOGP_CUDA_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
+    BOGP_CUDA_CHECK(cudaMalloc(&c->d_block_score, kMaxReduceBlocks * sizeof(double)));
+    BOGP_CUDA_CHECK(cudaMalloc(&c->d_block_index, kMaxReduceBlocks * sizeof(long long)));
+    BOGP_CUDA_CHECK(cudaMemset(c->d_scalars, 0, 64 * sizeof(double)));
+    BOGP_CUDA_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+    *out = c;
+    return BOGP_OK;
+}
+
+extern "C" void bogp_destroy(bogp_ctx* ctx) {
+    if (!ctx) return;
+    cudaFree(ctx->d_scalars); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_score); cudaFree(ctx->d_block_index);
+    delete ctx;
+}
+
+extern "C" int bogp_set_stream(bogp_ctx* ctx, void* cuda_stream) {
+    if (!ctx) { set_error("bogp_set_stream: null context"); return BOGP_ERR_BAD_ARG; }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return BOGP_OK;
+}
+extern "C" int bogp_sm_count(const bogp_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t bogp_launch_count(const bogp_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,505 @@
+// GP fit on B200: Gram matrix (K1), blocked fp64 Cholesky with DMMA trailing update (K2),
+// recursive triangular inverse W = L^-1, alpha = K^-1 y, log det, and the fragment-packed
+// copy of W that the acquisition kernel streams with bulk-TMA copies.
+//
+// Replaces np.linalg.inv / np.linalg.det / the quadratic form of the reference
+// (point_selector.py:79,89-90,117-119).
+#include "common.cuh"
+#include "gemm_f64.cuh"
+#include "fit.cuh"
+
+namespace bogp {
+
+// ------------------------------------------------------------------------------------------------
+// K1: ARD squared-exponential Gram matrix                                point_selector.py:166-195
+// 64x64 output tile per CTA, 4x4 elements per thread, points staged transposed in shared memory,
+// rows written as double2 pairs (each warp writes 512 contiguous bytes per row pair).
+// ------------------------------------------------------------------------------------------------
+struct GramArgs {
+    const double* a; const double* b; const double* inv_ell2;
+    double* k; int64_t ldk; int64_t na, nb; int dim; double jitter;
+    int64_t na_valid, nb_valid;   // rows/cols beyond these are identity padding (fit) -- pass na/nb for none
+    int lower_tiles_only;
+    int64_t strideK; int ell_stride;   // per blockIdx.z (batched multi-restart fit)
+};
+
+__global__ void __launch_bounds__(256) gram_kernel(GramArgs g) {
+    __shared__ double sa[BOGP_MAX_DIM][64];
+    __shared__ double sb[BOGP_MAX_DIM][64];
+    __shared__ double sl[BOGP_MAX_DIM];
+    const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+    if (g.lower_tiles_only && c0 > r0) return;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 64 * g.dim; i += 256) {
+        int p = i / g.dim, k = i % g.dim;
+        sa[k][p] = (r0 + p < g.na_valid) ? g.a[(r0 + p) * g.dim + k] : 0.0;
+        sb[k][p] = (c0 + p < g.nb_valid) ? g.b[(c0 + p) * g.dim + k] : 0.0;
+    }
+    if (tid < g.dim) sl[tid] = g.inv_ell2[(int64_t)blockIdx.z * g.ell_stride + tid];
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    double s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s[i][j] = 0.0;
+    for (int k = 0; k < g.dim; k++) {
+        double av[4], bv[4];
+        const double l = sl[k];
+#pragma unroll
+        for (int i = 0; i < 4; i++) av[i] = sa[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bv[j] = sb[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { double df = av[i] - bv[j]; s[i][j] += (df * df) * l; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t r = r0 + ty * 4 + i;
+        if (r >= g.na) continue;
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t c = c0 + tx * 4 + j;
+            const bool pad = (r >= g.na_valid) || (c >= g.nb_valid);
+            double e = pad ? 0.0 : exp(-0.5 * s[i][j]);
+            if (r == c) e = pad ? 1.0 : e + g.jitter;
+            v[j] = e;
+        }
+        const int64_t c = c0 + tx * 4;
+        double* out = g.k + (int64_t)blockIdx.z * g.strideK + r * g.ldk + c;
+        if (c + 3 < g.nb && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+            reinterpret_cast<double2*>(out)[0] = make_double2(v[0], v[1]);
+            reinterpret_cast<double2*>(out)[1] = make_double2(v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (c + j < g.nb) out[j] = v[j];
+        }
+    }
+}
+
+__global__ void inv_ell2_kernel(const double* ell, double* out, int64_t count) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) { double l = ell[k]; out[k] = 1.0 / (l * l); }
+}
+
+int launch_gram(bogp_ctx* ctx, const double* d_a, int64_t na, int64_t na_valid, const double* d_b, int64_t nb,
+                int64_t nb_valid, int dim, const double* d_inv_ell2, double jitter, double* d_k, int64_t ldk,
+                bool lower_tiles_only, int batch, int64_t strideK) {
+    GramArgs g{d_a, d_b, d_inv_ell2, d_k, ldk, na, nb, dim, jitter, na_valid, nb_valid, lower_tiles_only ? 1 : 0,
+               strideK, batch > 1 ? dim : 0};
+    dim3 grid((unsigned)((nb + 63) / 64), (unsigned)((na + 63) / 64), (unsigned)batch);
+    gram_kernel<<<grid, 256, 0, ctx->stream>>>(g);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+int launch_inv_ell2(bogp_ctx* ctx, const double* d_ell, double* d_out, int64_t count) {
+    inv_ell2_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d_ell, d_out, count);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 diagonal block: 64x64 Cholesky + inverse of the factor, one CTA per matrix of the batch.
+// The pivot is broadcast through shared memory; the 4 partial sums of each inverse entry are
+// combined with warp shuffles.
+// ------------------------------------------------------------------------------------------------
+struct DiagArgs {
+    double* a; int64_t lda; int64_t strideA;
+    double* w; int64_t ldw; int64_t strideW;
+    double* logdet; int* info; int kblk;
+};
+
+__global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
+    constexpr int NB = kDiagNB, LD = NB + 1;
+    extern __shared__ __align__(16) double diag_smem[];
+    double* a = diag_smem;
+    double* x = a + NB * LD;
+    double* dg = x + NB * LD;
+    const int tid = threadIdx.x;
+    double* A = g.a + blockIdx.x * g.strideA + (int64_t)g.kblk * NB * (g.lda + 1);
+    for (int i = tid; i < NB * NB; i += 256) {
+        int r = i / NB, c = i % NB;
+        a[r * LD + c] = (c <= r) ? A[(int64_t)r * g.lda + c] : 0.0;
+        x[r * LD + c] = 0.0;
+    }
+    bool bad = false;
+    for (int j = 0; j < NB; j++) {
+        __syncthreads();
+        const double ajj = a[j * LD + j];
+        if (!(ajj > 0.0) || isinf(ajj)) bad = true;
+        const double d = sqrt(ajj);
+        if (tid == j) dg[j] = d;
+        if (tid > j && tid < NB) a[tid * LD + j] = a[tid * LD + j] / d;
+        __syncthreads();
+        const int rem = NB - 1 - j;
+        for (int idx = tid; idx < rem * rem; idx += 256) {
+            int i = j + 1 + idx / rem, l = j + 1 + idx % rem;
+            if (l <= i) a[i * LD + l] -= a[i * LD + j] * a[l * LD + j];
+        }
+        if (bad && tid == 0) { atomicCAS(g.info + blockIdx.x, 0, g.kblk * NB + j + 1); }
+        bad = false;
+    }
+    __syncthreads();
+    if (tid < NB) a[tid * LD + tid] = dg[tid];
+    __syncthreads();
+    // X = L^-1, column c by forward substitution; 4 lanes share one column.
+    {
+        const int c = tid >> 2, q = tid & 3;
+        if (q == 0) x[c * LD + c] = 1.0 / dg[c];
+        __syncwarp();
+        for (int i = 1; i < NB; i++) {
+            double s = 0.0;
+            if (i > c) for (int k = c + q; k < i; k += 4) s += a[i * LD + k] * x[k * LD + c];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (i > c && q == 0) x[i * LD + c] = -s / dg[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* W = g.w ? g.w + blockIdx.x * g.strideW + (int64_t)g.kblk * NB * (g.ldw + 1) : nullptr;
+    for (int i = tid; i < NB * NB; i += 256) {
+        int r = i / NB, c = i % NB;
+        if (c <= r) A[(int64_t)r * g.lda + c] = a[r * LD + c];
+        if (W) W[(int64_t)r * g.ldw + c] = x[r * LD + c];
+    }
+    if (tid < 32 && g.logdet) {   // fixed-order sum of 2*log(d_j)
+        double s = 0.0;
+        if (tid == 0) { for (int j = 0; j < NB; j++) s += 2.0 * log(dg[j]); g.logdet[blockIdx.x] += s; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky, batch of `batch` matrices (strides in doubles).
+// ------------------------------------------------------------------------------------------------
+int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
+                     int64_t strideW, double* d_logdet, int* d_info, int batch) {
+    if (n % kDiagNB != 0) { set_error("cholesky: n=%lld is not a multiple of %d", (long long)n, kDiagNB); return BOGP_ERR_BAD_ARG; }
+    const int nblk = (int)(n / kDiagNB);
+    constexpr size_t kDiagSmem = (size_t)(2 * kDiagNB * (kDiagNB + 1) + kDiagNB) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
+        configured = true;
+    }
+    for (int kb = 0; kb < nblk; kb++) {
+        DiagArgs dg{d_a, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, kb};
+        chol_diag_kernel<<<batch, 256, kDiagSmem, ctx->stream>>>(dg);
+        BOGP_LAUNCH_CHECK(ctx);
+        const int below = (int)(n - (int64_t)(kb + 1) * kDiagNB);
+        if (below <= 0) break;
+        double* panel = d_a + (int64_t)(kb + 1) * kDiagNB * lda + (int64_t)kb * kDiagNB;
+        const double* dinv = d_w + (int64_t)kb * kDiagNB * (ldw + 1);
+        GemmArgs t{};   // panel <- panel * Dinv^T   (in place: one CTA owns complete rows, K fully staged before the stores)
+        t.A = panel; t.lda = lda; t.strideA = strideA;
+        t.B = dinv;  t.ldb = ldw; t.strideB = strideW;
+        t.C = panel; t.ldc = lda; t.strideC = strideA;
+        t.M = below; t.N = kDiagNB; t.K = kDiagNB; t.alpha = 1.0; t.accumulate = 0; t.lower_only = 0;
+        int rc = launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, t, batch);
+        if (rc) return rc;
+        GemmArgs s{};   // trailing -= panel * panel^T   (lower part only)
+        s.A = panel; s.lda = lda; s.strideA = strideA;
+        s.B = panel; s.ldb = lda; s.strideB = strideA;
+        s.C = d_a + (int64_t)(kb + 1) * kDiagNB * (lda + 1); s.ldc = lda; s.strideC = strideA;
+        s.M = below; s.N = below; s.K = kDiagNB; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
+        rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, s, batch);
+        if (rc) return rc;
+    }
+    return BOGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// W = L^-1 by recursive doubling: the 64-blocks on the diagonal of W are already inverted
+// (chol_diag_kernel); each level merges neighbouring inverted blocks,
+//   W21 = -W22 * (L21 * W11),
+// as two batched GEMMs that skip the structurally-zero k range.
+// `d_t` needs trtri_scratch_doubles(n) doubles per matrix.
+// ------------------------------------------------------------------------------------------------
+size_t trtri_scratch_doubles(int64_t n) {
+    size_t need = 0;
+    for (int64_t b = kDiagNB; b < n; b *= 2) {
+        int64_t full = 0; bool ragged = false;
+        for (int64_t o = 0; o + b < n; o += 2 * b) { if (o + 2 * b <= n) full++; else ragged = true; }
+        size_t t = (size_t)(full + (ragged ? 1 : 0)) * b * b;
+        if (t > need) need = t;
+    }
+    return need;
+}
+
+int trtri_recursive(bogp_ctx* ctx, const double* d_l, int64_t ldl, int64_t strideL, double* d_w, int64_t ldw,
+                    int64_t strideW, double* d_t, int64_t strideT, int64_t n, int batch) {
+    for (int64_t b = kDiagNB; b < n; b *= 2) {
+        int64_t full = 0; int64_t ragged_o = -1;
+        for (int64_t o = 0; o + b < n; o += 2 * b) { if (o + 2 * b <= n) full++; else ragged_o = o; }
+        for (int pass = 0; pass < 2; pass++) {
+            int64_t npairs, o0, r;
+            if (pass == 0) { npairs = full; o0 = 0; r = b; }
+            else { if (ragged_o < 0) break; npairs = 1; o0 = ragged_o; r = n - ragged_o - b; }
+            if (npairs == 0) continue;
+            {
+                // blockIdx.z = matrix * npairs + pair
+                const double* L  = d_l;
+                double*       W  = d_w;
+                double*       T  = d_t + (pass == 1 ? (size_t)full * b * b : 0);
+                GemmArgs g1{};
+                g1.inner = (int)npairs; g1.strideA2 = strideL; g1.strideB2 = strideW; g1.strideC2 = strideT;
+                g1.A = L + (o0 + b) * ldl + o0; g1.lda = ldl; g1.strideA = 2 * b * (ldl + 1);
+                g1.B = W + o0 * (ldw + 1);      g1.ldb = ldw; g1.strideB = 2 * b * (ldw + 1);
+                g1.C = T;                        g1.ldc = b;   g1.strideC = b * b;
+                g1.M = (int)r; g1.N = (int)b; g1.K = (int)b; g1.alpha = 1.0; g1.accumulate = 0; g1.lower_only = 0;
+                int rc = launch_gemm<128, 128, A_MK, B_KN, K_GE_N>(ctx, g1, (int)npairs * batch);
+                if (rc) return rc;
+                GemmArgs g2{};
+                g2.inner = (int)npairs; g2.strideA2 = strideW; g2.strideB2 = strideT; g2.strideC2 = strideW;
+                g2.A = W + (o0 + b) * (ldw + 1); g2.lda = ldw; g2.strideA = 2 * b * (ldw + 1);
+                g2.B = T;                         g2.ldb = b;   g2.strideB = b * b;
+                g2.C = W + (o0 + b) * ldw + o0;   g2.ldc = ldw; g2.strideC = 2 * b * (ldw + 1);
+                g2.M = (int)r; g2.N = (int)b; g2.K = (int)r; g2.alpha = -1.0; g2.accumulate = 0; g2.lower_only = 0;
+                rc = launch_gemm<128, 128, A_MK, B_KN, K_LE_M>(ctx, g2, (int)npairs * batch);
+                if (rc) return rc;
+            }
+        }
+    }
+    return BOGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// alpha = W^T (W y) with fixed summation order, y^T alpha, nlml.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ w, int64_t ldw, int64_t strideW,
+                                                         const double* __restrict__ y, double* __restrict__ v, int n) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    w += blockIdx.y * strideW; v += (int64_t)blockIdx.y * n;     // y is shared by the batch
+    const double* wr = w + (int64_t)row * ldw;
+    double s = 0.0;
+    for (int j = lane; j <= row; j += 32) s += wr[j] * y[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) v[row] = s;
+}
+
+// alpha_j = sum_{i >= j} W[i][j] v[i]; block = 32 columns x 8 row-slices, slices combined in order.
+__global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restrict__ w, int64_t ldw, int64_t strideW,
+                                                           const double* __restrict__ v, double* __restrict__ alpha, int n) {
+    __shared__ double part[8][33];
+    w += blockIdx.y * strideW; v += (int64_t)blockIdx.y * n; alpha += (int64_t)blockIdx.y * n;
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    const int rows = n - c0, per = (rows + 7) / 8;
+    const int rb = c0 + sl * per, re = min(n, rb + per);
+    double s = 0.0;
+    if (col < n) for (int i = max(rb, col); i < re; i++) s += w[(int64_t)i * ldw + col] * v[i];
+    part[sl][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (sl == 0 && col < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += part[k][threadIdx.x];
+        alpha[col] = t;
+    }
+}
+
+int launch_alpha(bogp_ctx* ctx, const double* d_w, int64_t ldw, int64_t strideW, const double* d_y, double* d_v,
+                 double* d_alpha, int n, int batch) {
+    trmv_lower_kernel<<<dim3((unsigned)((n + 7) / 8), batch), 256, 0, ctx->stream>>>(d_w, ldw, strideW, d_y, d_v, n);
+    BOGP_LAUNCH_CHECK(ctx);
+    trmv_lower_t_kernel<<<dim3((unsigned)((n + 31) / 32), batch), 256, 0, ctx->stream>>>(d_w, ldw, strideW, d_v, d_alpha, n);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+// scalars[1] = y . alpha ; scalars[2] = 0.5*(y.alpha + logdet + n log 2pi)   (point_selector.py:119)
+__global__ void __launch_bounds__(256) nlml_finish_kernel(const double* __restrict__ y, const double* __restrict__ alpha, int n_pad,
+                                                          int n, double* scalars) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_pad; i += 256) s += y[i] * alpha[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) {
+        scalars[1] = red[0];
+        scalars[2] = 0.5 * (red[0] + scalars[0] + (double)n * log(2.0 * 3.14159265358979323846));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pack W (row-major, lower) into DMMA-fragment order for the acquisition kernel:
+// tile (ib, kt) = rows [256 ib, +256) x k [16 kt, +16), 0 <= kt < 16 (ib+1); inside a tile
+// element (m, k) sits at ((k/4 % 4) * 32 + m/8) * 32 + (m % 8) * 4 + k % 4, so that a warp's
+// A fragment is one contiguous 256-byte line and a whole tile is one 32 KB bulk copy.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_w_kernel(const double* __restrict__ w, int64_t ldw, double* __restrict__ wp) {
+    __shared__ double t[kAcqBM][kAcqKB + 1];
+    const int ib = blockIdx.y, kt = blockIdx.x;
+    if (kt >= (ib + 1) * (kAcqBM / kAcqKB)) return;
+    const int64_t tile = (int64_t)ib * (ib + 1) / 2 * (kAcqBM / kAcqKB) + kt;
+    const double* src = w + (int64_t)ib * kAcqBM * ldw + (int64_t)kt * kAcqKB;
+    for (int i = threadIdx.x; i < kAcqBM * kAcqKB; i += 256) {
+        int m = i / kAcqKB, k = i % kAcqKB;
+        t[m][k] = src[(int64_t)m * ldw + k];
+    }
+    __syncthreads();
+    double* dst = wp + tile * (kAcqBM * kAcqKB);
+    for (int i = threadIdx.x; i < kAcqBM * kAcqKB; i += 256) {
+        int lane = i & 31, m8 = (i >> 5) & 31, kk = i >> 10;
+        dst[i] = t[m8 * 8 + (lane >> 2)][kk * 4 + (lane & 3)];
+    }
+}
+
+size_t packed_w_doubles(int64_t n_pad) {
+    const int64_t nI = n_pad / kAcqBM;
+    return (size_t)(nI * (nI + 1) / 2) * kAcqBM * kAcqBM;
+}
+
+__global__ void pad_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t n_pad, int width) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * width) return;
+    dst[i] = (i / width < n) ? src[i] : 0.0;
+}
+
+__global__ void zero_kernel(double* p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = 0.0;
+}
+
+}  // namespace bogp
+
+using namespace bogp;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+struct bogp_fit {
+    int64_t n, n_pad; int dim;
+    double *x_pad, *y_pad, *inv_ell2, *a, *w, *wp, *t, *alpha, *v, *scalars;
+    int* info;
+    double jitter;
+    bogp_ctx* ctx;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct FitLayout { size_t x, y, ell, a, w, wp, alpha, v, scal, info, total; };
+static FitLayout fit_layout(int64_t n, int dim) {
+    const int64_t np = (n + kPad - 1) / kPad * kPad;
+    FitLayout l{}; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    l.x = take(np * dim * 8); l.y = take(np * 8); l.ell = take(BOGP_MAX_DIM * 8);
+    l.a = take((size_t)np * np * 8); l.w = take((size_t)np * np * 8);
+    size_t shared = packed_w_doubles(np); size_t tneed = trtri_scratch_doubles(np);
+    // the trtri scratch and the packed W are never live at the same time -> but keep them
+    // separate when the scratch is the larger one (ragged block counts)
+    l.wp = take((shared > tneed ? shared : tneed) * 8);
+    l.alpha = take(np * 8); l.v = take(np * 8); l.scal = take(64 * 8); l.info = take(64 * 4);
+    l.total = off;
+    return l;
+}
+
+extern "C" size_t bogp_fit_workspace_bytes(int64_t n, int dim) {
+    if (n <= 0 || dim <= 0 || dim > BOGP_MAX_DIM) return 0;
+    return fit_layout(n, dim).total;
+}
+
+extern "C" int bogp_kernel_matrix(bogp_ctx* ctx, const double* d_a, int64_t na, const double* d_b, int64_t nb, int dim,
+                                  const double* d_ell, double jitter, double* d_k, int64_t ldk) {
+    if (!ctx || !d_a || !d_b || !d_ell || !d_k || na <= 0 || nb <= 0 || dim <= 0 || dim > BOGP_MAX_DIM || ldk < nb) {
+        set_error("bogp_kernel_matrix: bad argument"); return BOGP_ERR_BAD_ARG;
+    }
+    int rc = launch_inv_ell2(ctx, d_ell, ctx->d_scalars + 32, dim);
+    if (rc) return rc;
+    return launch_gram(ctx, d_a, na, na, d_b, nb, nb, dim, ctx->d_scalars + 32, jitter, d_k, ldk, false, 1, 0);
+}
+
+extern "C" int bogp_cholesky(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, double* d_linv, double* d_logdet, int* d_info) {
+    if (!ctx || !d_a || !d_linv || !d_logdet || !d_info || n <= 0 || lda < n) { set_error("bogp_cholesky: bad argument"); return BOGP_ERR_BAD_ARG; }
+    BOGP_CUDA_CHECK(cudaMemsetAsync(d_logdet, 0, sizeof(double), ctx->stream));
+    BOGP_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+    return cholesky_blocked(ctx, d_a, n, lda, 0, d_linv, lda, 0, d_logdet, d_info, 1);
+}
+
+extern "C" int bogp_fit_create(bogp_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int dim, const double* d_ell,
+                               double jitter, void* d_workspace, size_t workspace_bytes, bogp_fit** out, double* h_nlml_out) {
+    if (!ctx || !d_x || !d_y || !d_ell || !d_workspace || !out || n <= 0 || dim <= 0 || dim > BOGP_MAX_DIM) {
+        set_error("bogp_fit_create: bad argument"); return BOGP_ERR_BAD_ARG;
+    }
+    const FitLayout l = fit_layout(n, dim);
+    if (workspace_bytes < l.total) { set_error("bogp_fit_create: workspace %zu < %zu bytes", workspace_bytes, l.total); return BOGP_ERR_WORKSPACE; }
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) != 0) { set_error("bogp_fit_create: workspace must be 256-byte aligned"); return BOGP_ERR_BAD_ARG; }
+    char* base = static_cast<char*>(d_workspace);
+    bogp_fit* f = new bogp_fit();
+    f->ctx = ctx; f->n = n; f->dim = dim; f->jitter = jitter;
+    const int64_t np = (n + kPad - 1) / kPad * kPad; f->n_pad = np;
+    f->x_pad = (double*)(base + l.x); f->y_pad = (double*)(base + l.y); f->inv_ell2 = (double*)(base + l.ell);
+    f->a = (double*)(base + l.a); f->w = (double*)(base + l.w); f->wp = (double*)(base + l.wp); f->t = f->wp;
+    f->alpha = (double*)(base + l.alpha); f->v = (double*)(base + l.v); f->scalars = (double*)(base + l.scal); f->info = (int*)(base + l.info);
+    cudaStream_t st = ctx->stream;
+    int rc;
+#define FIT_TRY(e) do { rc = (e); if (rc) { delete f; return rc; } } while (0)
+#define FIT_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s: %s", #e, cudaGetErrorString(_e)); delete f; return BOGP_ERR_CUDA; } } while (0)
+    FIT_CUDA(cudaMemsetAsync(f->scalars, 0, 64 * 8, st));
+    FIT_CUDA(cudaMemsetAsync(f->info, 0, 64 * 4, st));
+    FIT_CUDA(cudaMemsetAsync(f->w, 0, (size_t)np * np * 8, st));
+    pad_copy_kernel<<<(unsigned)((np * dim + 255) / 256), 256, 0, st>>>(d_x, f->x_pad, n, np, dim); ctx->launches++;
+    pad_copy_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(d_y, f->y_pad, n, np, 1); ctx->launches++;
+    FIT_TRY(launch_inv_ell2(ctx, d_ell, f->inv_ell2, dim));
+    // K1 (lower tiles; identity in the padding)
+    FIT_TRY(launch_gram(ctx, f->x_pad, np, n, f->x_pad, np, n, dim, f->inv_ell2, jitter, f->a, np, true, 1, 0));
+    // K2
+    FIT_TRY(cholesky_blocked(ctx, f->a, np, np, 0, f->w, np, 0, f->scalars, f->info, 1));
+    // W = L^-1
+    FIT_TRY(trtri_recursive(ctx, f->a, np, 0, f->w, np, 0, f->t, 0, np, 1));
+    // alpha = W^T W y
+    FIT_TRY(launch_alpha(ctx, f->w, np, 0, f->y_pad, f->v, f->alpha, (int)np, 1));
+    nlml_finish_kernel<<<1, 256, 0, st>>>(f->y_pad, f->alpha, (int)np, (int)n, f->scalars); ctx->launches++;
+    // packed W (overwrites the trtri scratch)
+    {
+        const int nI = (int)(np / kAcqBM);
+        dim3 grid(nI * (kAcqBM / kAcqKB), nI);
+        pack_w_kernel<<<grid, 256, 0, st>>>(f->w, np, f->wp); ctx->launches++;
+    }
+    FIT_CUDA(cudaGetLastError());
+    // status + nlml back to the host
+    int info = 0; double sc[3];
+    FIT_CUDA(cudaMemcpyAsync(&info, f->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FIT_CUDA(cudaMemcpyAsync(sc, f->scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    FIT_CUDA(cudaStreamSynchronize(st));
+    if (info != 0) {
+        set_error("bogp_fit_create: matrix not positive definite (pivot %d of %lld)", info, (long long)n);
+        delete f; return BOGP_ERR_NOT_POSDEF;
+    }
+    if (h_nlml_out) *h_nlml_out = sc[2];
+    *out = f;
+    return BOGP_OK;
+#undef FIT_TRY
+#undef FIT_CUDA
+}
+
+extern "C" void bogp_fit_destroy(bogp_fit* fit) { delete fit; }
+extern "C" int64_t bogp_fit_n_pad(const bogp_fit* fit) { return fit ? fit->n_pad : 0; }
+extern "C" const double* bogp_fit_chol(const bogp_fit* fit) { return fit ? fit->a : nullptr; }
+extern "C" const double* bogp_fit_linv(const bogp_fit* fit) { return fit ? fit->w : nullptr; }
+extern "C" const double* bogp_fit_alpha(const bogp_fit* fit) { return fit ? fit->alpha : nullptr; }
+extern "C" double bogp_fit_logdet(const bogp_fit* fit) {
+    if (!fit) return 0.0;
+    double v = 0.0;
+    cudaMemcpyAsync(&v, fit->scalars, sizeof(double), cudaMemcpyDeviceToHost, fit->ctx->stream);
+    cudaStreamSynchronize(fit->ctx->stream);
+    return v;
+}
+
+// accessors used by acquire.cu
+namespace bogp {
+const double* fit_wp(const bogp_fit* f) { return f->wp; }
+const double* fit_xpad(const bogp_fit* f) { return f->x_pad; }
+const double* fit_inv_ell2(const bogp_fit* f) { return f->inv_ell2; }
+const double* fit_alpha(const bogp_fit* f) { return f->alpha; }
+int64_t fit_n(const bogp_fit* f) { return f->n; }
+int fit_dim(const bogp_fit* f) { return f->dim; }
+}

@@ -1,0 +1,30 @@
+// Internal interfaces between the translation units of libbogp.
+#pragma once
+#include "common.cuh"
+
+struct bogp_fit;
+
+namespace bogp {
+
+int launch_gram(bogp_ctx* ctx, const double* d_a, int64_t na, int64_t na_valid, const double* d_b, int64_t nb,
+                int64_t nb_valid, int dim, const double* d_inv_ell2, double jitter, double* d_k, int64_t ldk,
+                bool lower_tiles_only, int batch, int64_t strideK);
+int launch_inv_ell2(bogp_ctx* ctx, const double* d_ell, double* d_out, int64_t count);
+int launch_alpha(bogp_ctx* ctx, const double* d_w, int64_t ldw, int64_t strideW, const double* d_y, double* d_v,
+                 double* d_alpha, int n, int batch);
+
+int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
+                     int64_t strideW, double* d_logdet, int* d_info, int batch);
+size_t trtri_scratch_doubles(int64_t n);
+int trtri_recursive(bogp_ctx* ctx, const double* d_l, int64_t ldl, int64_t strideL, double* d_w, int64_t ldw,
+                    int64_t strideW, double* d_t, int64_t strideT, int64_t n, int batch);
+size_t packed_w_doubles(int64_t n_pad);
+
+const double* fit_wp(const bogp_fit* f);
+const double* fit_xpad(const bogp_fit* f);
+const double* fit_inv_ell2(const bogp_fit* f);
+const double* fit_alpha(const bogp_fit* f);
+int64_t fit_n(const bogp_fit* f);
+int fit_dim(const bogp_fit* f);
+
+}  // namespace bogp

@@ -1,0 +1,273 @@
+"""Host side of the B200 GP engine: device memory and streams via torch, arithmetic via libbogp.
+
+`GPEngine` is the thin Python layer between the reference-facing `PointSelector` drop-in
+(`point_selector.py`) and the C ABI (`include/bogp.h`).  torch is plumbing only: it owns the
+HBM buffers and the CUDA stream; every number is produced by the hand-written sm_100a
+kernels of `csrc/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACQ_EI, ACQ_LCB, BogpError, Candidates
+
+# reference jitters: kernel_rbf adds 1e-4 (point_selector.py:193), update_surrogate another 1e-6 (:78-79)
+JITTER_LML = 1e-4
+PRIOR_DIAG = (1.0 + 1e-4) + 1e-6            # diag of cov_pred, same rounding order as the reference
+JITTER_POSTERIOR = PRIOR_DIAG - 1.0         # exact: 1.0 + JITTER_POSTERIOR == PRIOR_DIAG bit for bit
+
+
+@dataclass
+class CandidateGrid:
+    """Row-major Cartesian product of `axes`, axis 0 slowest (select_parameters.py:273-279).
+    Never materialised: the kernels turn a flat index into coordinates on the fly."""
+    axes: Sequence[np.ndarray]
+
+    @property
+    def shape(self):
+        return [len(a) for a in self.axes]
+
+    @property
+    def size(self):
+        return int(np.prod([len(a) for a in self.axes], dtype=np.int64))
+
+    @property
+    def dim(self):
+        return len(self.axes)
+
+
+@dataclass
+class AcquireResult:
+    best_score: float
+    best_index: int
+    mu: Optional[torch.Tensor] = None
+    sigma: Optional[torch.Tensor] = None
+    acq: Optional[torch.Tensor] = None
+
+
+class GPFit:
+    """Fitted surrogate: Cholesky factor, W = L^-1 (packed), alpha -- all resident in HBM."""
+
+    def __init__(self, engine, handle, workspace, n, dim, nlml, ell, jitter):
+        self.engine, self._h, self._ws = engine, handle, workspace
+        self.n, self.dim, self.nlml, self.ell, self.jitter = n, dim, nlml, ell, jitter
+
+    @property
+    def n_pad(self):
+        return int(self.engine.lib.bogp_fit_n_pad(self._h))
+
+    @property
+    def logdet(self):
+        return float(self.engine.lib.bogp_fit_logdet(self._h))
+
+    def _view(self, ptr, numel):
+        base = self._ws.data_ptr()
+        off = ptr - base
+        return self._ws[off:off + numel * 8].view(torch.float64)
+
+    def chol(self):
+        """L as an (n_pad, n_pad) tensor view (lower triangle valid)."""
+        npad = self.n_pad
+        return self._view(self.engine.lib.bogp_fit_chol(self._h), npad * npad).view(npad, npad)
+
+    def linv(self):
+        npad = self.n_pad
+        return self._view(self.engine.lib.bogp_fit_linv(self._h), npad * npad).view(npad, npad)
+
+    def alpha(self):
+        return self._view(self.engine.lib.bogp_fit_alpha(self._h), self.n_pad)[: self.n]
+
+    def close(self):
+        if self._h:
+            self.engine.lib.bogp_fit_destroy(self._h)
+            self._h = None
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GPEngine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("bayesian_optimisation_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        _lib.check(self.lib.bogp_create(device, C.byref(h)))
+        self._ctx = h
+        self._acq_ws = None
+        self._sync_stream()
+
+    # ------------------------------------------------------------------ plumbing
+    def _sync_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.bogp_set_stream(self._ctx, C.c_void_p(s)))
+
+    def to_device(self, a, dtype=torch.float64):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.bogp_launch_count(self._ctx))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.bogp_sm_count(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.bogp_destroy(self._ctx)
+            self._ctx = None
+
+    # ------------------------------------------------------------------ K1
+    def kernel_matrix(self, a, b, ell, jitter: float = 0.0) -> torch.Tensor:
+        """exp(-0.5 sum_k (a_ik-b_jk)^2/ell_k^2) (+ jitter on i == j)   point_selector.py:166-195"""
+        self._sync_stream()
+        da, db, dl = self.to_device(a), self.to_device(b), self.to_device(np.asarray(ell, dtype=np.float64).reshape(-1))
+        na, dim = da.shape
+        nb = db.shape[0]
+        out = torch.empty((na, nb), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bogp_kernel_matrix(self._ctx, da.data_ptr(), na, db.data_ptr(), nb, dim, dl.data_ptr(),
+                                               float(jitter), out.data_ptr(), nb))
+        return out
+
+    # ------------------------------------------------------------------ K2 + fit
+    def cholesky(self, a: torch.Tensor):
+        """In-place blocked Cholesky of the lower triangle of `a` (n multiple of 64).
+        Returns (logdet, info)."""
+        self._sync_stream()
+        n = a.shape[0]
+        linv = torch.zeros_like(a)
+        scal = torch.zeros(1, dtype=torch.float64, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.bogp_cholesky(self._ctx, a.data_ptr(), n, a.stride(0), linv.data_ptr(), scal.data_ptr(), info.data_ptr()))
+        return float(scal.item()), int(info.item())
+
+    def fit(self, x, y, ell, jitter: float = JITTER_POSTERIOR) -> GPFit:
+        """K = k(X,X) + jitter I; Cholesky; alpha; W = L^-1      point_selector.py:79,89-90"""
+        self._sync_stream()
+        dx, dy = self.to_device(x), self.to_device(np.asarray(y, dtype=np.float64).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1))
+        ell_np = np.asarray(ell.cpu() if isinstance(ell, torch.Tensor) else ell, dtype=np.float64).reshape(-1)
+        dl = self.to_device(ell_np)
+        n, dim = dx.shape
+        if dl.numel() != dim:
+            raise ValueError(f"{dl.numel()} length scales for {dim} features")
+        nbytes = self.lib.bogp_fit_workspace_bytes(n, dim)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        h = C.c_void_p()
+        nlml = C.c_double()
+        code = self.lib.bogp_fit_create(self._ctx, dx.data_ptr(), dy.data_ptr(), n, dim, dl.data_ptr(), float(jitter),
+                                        ws.data_ptr(), nbytes, C.byref(h), C.byref(nlml))
+        if code == _lib.BOGP_ERR_NOT_POSDEF:
+            raise np.linalg.LinAlgError(self.lib.bogp_last_error().decode())
+        _lib.check(code)
+        return GPFit(self, h, ws, n, dim, nlml.value, ell_np, float(jitter))
+
+    # ------------------------------------------------------------------ K4
+    def acquire(self, fit: GPFit, candidates, c_begin: int = 0, c_end: Optional[int] = None, kind: int = ACQ_LCB,
+                explore: float = 4.0, f_best: float = 0.0, prior_diag: float = PRIOR_DIAG, outputs: bool = False,
+                chunk: int = 8192, cross_jitter: float = 0.0) -> AcquireResult:
+        """Score flat candidate indices [c_begin, c_end) and return the best (score, index).
+
+        `candidates`: CandidateGrid, or an explicit (C, d) array (numpy -> copied to HBM, or a
+        CUDA tensor used in place)."""
+        self._sync_stream()
+        keep = []
+        cd = Candidates()
+        cd.cross_jitter = float(cross_jitter)
+        if isinstance(candidates, CandidateGrid):
+            if candidates.dim != fit.dim:
+                raise ValueError("candidate grid dimension does not match the fit")
+            axes = self.to_device(np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1) for a in candidates.axes]))
+            lens = (C.c_int32 * candidates.dim)(*candidates.shape)
+            keep += [axes, lens]
+            cd.d_points, cd.d_axes, cd.h_axis_len, cd.c_total = None, axes.data_ptr(), lens, candidates.size
+        else:
+            pts = self.to_device(candidates)
+            if pts.ndim != 2 or pts.shape[1] != fit.dim:
+                raise ValueError("candidates must be (C, d)")
+            keep.append(pts)
+            cd.d_points, cd.d_axes, cd.h_axis_len, cd.c_total = pts.data_ptr(), None, None, pts.shape[0]
+        total = int(cd.c_total)
+        c_end = total if c_end is None else int(c_end)
+        count = c_end - int(c_begin)
+        chunk = max(64, min(int(chunk), (count + 63) // 64 * 64))
+        need = self.lib.bogp_acquire_workspace_bytes(fit._h, chunk)
+        if self._acq_ws is None or self._acq_ws.numel() < need:
+            self._acq_ws = None
+            self._acq_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        mu = sigma = acq = None
+        if outputs:
+            mu = torch.empty(count, dtype=torch.float64, device=self.device)
+            sigma = torch.empty_like(mu)
+            acq = torch.empty_like(mu)
+        bs, bi = C.c_double(), C.c_int64()
+        code = self.lib.bogp_acquire(self._ctx, fit._h, C.byref(cd), int(c_begin), c_end, int(kind), float(explore),
+                                     float(f_best), float(prior_diag),
+                                     mu.data_ptr() if outputs else None, sigma.data_ptr() if outputs else None,
+                                     acq.data_ptr() if outputs else None,
+                                     self._acq_ws.data_ptr(), need, C.byref(bs), C.byref(bi))
+        if code == _lib.BOGP_ERR_NAN_SCORE:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0 (NaN acquisition value)")
+        _lib.check(code)
+        del keep
+        return AcquireResult(bs.value, int(bi.value), mu, sigma, acq)
+
+    def score_argmax(self, mu: torch.Tensor, sigma: torch.Tensor, kind: int = ACQ_LCB, explore: float = 4.0,
+                     f_best: float = 0.0, want_acq: bool = True) -> AcquireResult:
+        """acquisition + first arg-max on device-resident mu/sigma   point_selector.py:197-207"""
+        self._sync_stream()
+        mu, sigma = self.to_device(mu).reshape(-1), self.to_device(sigma).reshape(-1)
+        acq = torch.empty_like(mu) if want_acq else None
+        bs, bi = C.c_double(), C.c_int64()
+        code = self.lib.bogp_score_argmax(self._ctx, mu.data_ptr(), sigma.data_ptr(), mu.numel(), int(kind), float(explore),
+                                          float(f_best), acq.data_ptr() if want_acq else None, C.byref(bs), C.byref(bi))
+        if code == _lib.BOGP_ERR_NAN_SCORE:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0 (NaN acquisition value)")
+        _lib.check(code)
+        return AcquireResult(bs.value, int(bi.value), mu, sigma, acq)
+
+    # ------------------------------------------------------------------ K3
+    def nlml_batched(self, x, y, ells, jitter: float = JITTER_LML, want_grad: bool = False):
+        """nlml (and d nlml/d ell) for R length-scale vectors at once   point_selector.py:111-138"""
+        self._sync_stream()
+        dx = self.to_device(x)
+        dy = self.to_device(np.asarray(y, dtype=np.float64).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1))
+        de = self.to_device(ells)
+        n, dim = dx.shape
+        if de.ndim != 2 or de.shape[1] != dim:
+            raise ValueError("ells must be (R, d)")
+        r = de.shape[0]
+        out = torch.empty(r, dtype=torch.float64, device=self.device)
+        grad = torch.empty((r, dim), dtype=torch.float64, device=self.device) if want_grad else None
+        need = self.lib.bogp_nlml_batched_workspace_bytes(n, dim, r, 1 if want_grad else 0)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.bogp_nlml_batched(self._ctx, dx.data_ptr(), dy.data_ptr(), n, dim, de.data_ptr(), r, float(jitter),
+                                              out.data_ptr(), grad.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel()))
+        torch.cuda.current_stream(self.device).synchronize()
+        return (out, grad) if want_grad else out
+
+
+_default_engine = None
+
+
+def default_engine() -> GPEngine:
+    """Process-wide engine on the current CUDA device (LOCAL_RANK under torchrun)."""
+    global _default_engine
+    if _default_engine is None:
+        import os
+        _default_engine = GPEngine(int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.device_count() > 1 else 0)
+    return _default_engine

@@ -1,0 +1,278 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors
+produced by the unmodified reference.  Tolerances (BASELINE.json north_star): posterior mean,
+variance and log marginal likelihood within 1e-9 relative in fp64; selected index exact."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle import gp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bayesian_optimisation_b200.engine import GPEngine
+    return GPEngine(0)
+
+
+def _consts():
+    from bayesian_optimisation_b200 import engine as e
+    return e
+
+
+def assert_var_close(got, want, cond=None, rtol=RTOL):
+    """sigma^2 = 1.000101 - k^T K^-1 k is a cancellation against the prior, so both the reference
+    (explicit inverse) and this path (Cholesky) carry an ABSOLUTE error ~ cond(K)*eps of the
+    prior: 1e-9 relative holds wherever sigma^2 >> cond*eps, and the absolute
+    floor below is max(2e-11, cond(K)*eps)."""
+    atol = 2e-11 if cond is None else max(2e-11, cond * np.finfo(np.float64).eps)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def cond_of(X, ell, jitter):
+    K = o.kernel_rbf_chunked(X, X, ell)
+    K[np.diag_indices_from(K)] += jitter
+    return float(np.linalg.cond(K))
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("name", golden_names("direct"))
+def test_kernel_matrix_matches_reference(eng, name):
+    g = load_golden(name)
+    e = _consts()
+    Kxx = eng.kernel_matrix(g["X"], g["X"], g["ell"], e.JITTER_LML).cpu().numpy()
+    np.testing.assert_allclose(Kxx, g["Kxx"], rtol=1e-13, atol=1e-300)
+    quirk = g["X"].shape == g["P"].shape
+    Kxp = eng.kernel_matrix(g["X"], g["P"], g["ell"], e.JITTER_LML if quirk else 0.0).cpu().numpy()
+    np.testing.assert_allclose(Kxp, g["Kxp"], rtol=1e-13, atol=1e-300)
+
+
+def test_kernel_matrix_odd_shapes(eng):
+    rng = np.random.default_rng(5)
+    for na, nb, d in [(1, 1, 1), (3, 130, 2), (65, 7, 5), (200, 257, 16)]:
+        A, B, ell = rng.random((na, d)), rng.random((nb, d)), 0.2 + rng.random(d)
+        K = eng.kernel_matrix(A, B, ell).cpu().numpy()
+        np.testing.assert_allclose(K, o.kernel_rbf_chunked(A, B, ell), rtol=1e-13, atol=1e-300)
+
+
+# ------------------------------------------------------------------ K2 / fit
+@pytest.mark.parametrize("n,d", [(64, 3), (256, 4), (1024, 6)])
+def test_cholesky_matches_numpy(eng, n, d):
+    import torch
+    X, y, ell = o.synthetic_problem(n, d, seed=n)
+    K = o.kernel_rbf(X, X, ell)
+    a = torch.from_numpy(K).cuda()
+    logdet, info = eng.cholesky(a)
+    assert info == 0
+    L = np.tril(a.cpu().numpy())
+    Lref = np.linalg.cholesky(K)
+    np.testing.assert_allclose(L, Lref, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(logdet, np.linalg.slogdet(K)[1], rtol=1e-12)
+
+
+def test_cholesky_reports_non_positive_definite(eng):
+    import torch
+    a = torch.eye(128, dtype=torch.float64).cuda()
+    a[70, 70] = -1.0
+    _, info = eng.cholesky(a)
+    assert info == 71
+    X = np.zeros((3, 2))
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.fit(X, np.ones(3), np.ones(2), jitter=-2.0)
+
+
+@pytest.mark.parametrize("n,d", [(5, 2), (200, 3), (300, 4), (1024, 6), (1300, 5)])
+def test_fit_state_matches_numpy(eng, n, d):
+    e = _consts()
+    X, y, ell = o.synthetic_problem(n, d, seed=7 + n)
+    fit = eng.fit(X, y, ell, e.JITTER_LML)
+    K = o.kernel_rbf(X, X, ell)
+    Lref = np.linalg.cholesky(K)
+    L = np.tril(fit.chol().cpu().numpy())[:n, :n]
+    np.testing.assert_allclose(L, Lref, rtol=1e-9, atol=1e-12)
+    W = np.tril(fit.linv().cpu().numpy())
+    np.testing.assert_allclose(W[:n, :n] @ Lref, np.eye(n), atol=1e-9)
+    if fit.n_pad > n:   # identity padding
+        np.testing.assert_array_equal(W[n:, n:], np.eye(fit.n_pad - n))
+        assert not W[n:, :n].any()
+    alpha = fit.alpha().cpu().numpy()
+    ref_alpha = np.linalg.inv(K) @ y
+    np.testing.assert_allclose(alpha, ref_alpha, rtol=1e-7, atol=1e-9 * np.abs(ref_alpha).max())
+    ref = o.nlml(X, y, ell, stable=True)
+    assert abs(fit.nlml - ref) <= RTOL * abs(ref)
+    np.testing.assert_allclose(fit.logdet, np.linalg.slogdet(K)[1], rtol=1e-11)
+
+
+# ------------------------------------------------------------------ K4
+@pytest.mark.parametrize("name", golden_names("direct"))
+def test_acquire_explicit_matches_reference(eng, name):
+    g = load_golden(name)
+    e = _consts()
+    X, y, P, ell = g["X"], g["y"], g["P"], g["ell"]
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    quirk = X.shape == P.shape
+    res = eng.acquire(fit, P, outputs=True, cross_jitter=e.JITTER_LML if quirk else 0.0)
+    mu, sig, acq = res.mu.cpu().numpy(), res.sigma.cpu().numpy(), res.acq.cpu().numpy()
+    np.testing.assert_allclose(mu, g["mean_func"], rtol=RTOL, atol=RTOL * np.abs(g["mean_func"]).max())
+    assert_var_close(sig ** 2, g["cov_func"] ** 2)
+    np.testing.assert_array_equal(acq, 4 * sig - mu)              # two roundings, exactly numpy's
+    assert res.best_index == int(g["index"][0])
+    assert res.best_score == acq[res.best_index]
+
+
+@pytest.mark.parametrize("n,d,G,chunk", [(1024, 6, 5, 4096), (300, 3, 21, 1000), (700, 8, 3, 8192)])
+def test_acquire_grid_matches_oracle(eng, n, d, G, chunk):
+    from bayesian_optimisation_b200.engine import CandidateGrid
+    e = _consts()
+    X, y, ell = o.synthetic_problem(n, d, seed=n + d)
+    axes = [np.linspace(0, 1, G + (k % 2)) for k in range(d)]      # ragged axis lengths
+    P = o.candidate_grid(axes)
+    mu_ref, var_ref = o.posterior_diag(X, y, P, ell, return_var=True)
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    res = eng.acquire(fit, CandidateGrid(axes), outputs=True, chunk=chunk)
+    mu, sig = res.mu.cpu().numpy(), res.sigma.cpu().numpy()
+    cond = cond_of(X, ell, e.JITTER_POSTERIOR)
+    print(f"cond(K) = {cond:.3g}")
+    np.testing.assert_allclose(mu, mu_ref, rtol=RTOL, atol=RTOL * np.abs(mu_ref).max())
+    assert_var_close(sig ** 2, var_ref, cond)
+    acq_ref = o.lcb(mu_ref, np.sqrt(np.abs(var_ref)))
+    assert res.best_index == int(o.first_argmax(acq_ref)[0])
+    # the same sweep on an explicit copy of the grid gives bit-identical numbers
+    res2 = eng.acquire(fit, P, outputs=True, chunk=chunk)
+    np.testing.assert_array_equal(res2.mu.cpu().numpy(), mu)
+    np.testing.assert_array_equal(res2.sigma.cpu().numpy(), sig)
+    assert res2.best_index == res.best_index
+
+
+def test_expected_improvement_matches_oracle(eng):
+    from bayesian_optimisation_b200.engine import ACQ_EI, CandidateGrid
+    e = _consts()
+    X, y, ell = o.synthetic_problem(512, 4, seed=11)
+    axes = [np.linspace(0, 1, 9)] * 4
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    fb = float(y.min())
+    res = eng.acquire(fit, CandidateGrid(axes), kind=ACQ_EI, f_best=fb, outputs=True)
+    mu, sig = res.mu.cpu().numpy(), res.sigma.cpu().numpy()
+    ei_ref = o.expected_improvement(mu, sig, fb)             # oracle formula on the device mu/sigma
+    np.testing.assert_allclose(res.acq.cpu().numpy(), ei_ref, rtol=1e-9, atol=1e-300)
+    mu_ref, var_ref = o.posterior_diag(X, y, o.candidate_grid(axes), ell, return_var=True)
+    ei_full = o.expected_improvement(mu_ref, np.sqrt(np.abs(var_ref)), fb)
+    assert res.best_index == int(np.flatnonzero(ei_full == ei_full.max())[0])
+
+
+def test_sharded_ranges_are_bit_identical_and_pick_the_same_index(eng):
+    from bayesian_optimisation_b200.engine import CandidateGrid
+    from bayesian_optimisation_b200.sharding import reduce_pairs, shard_range
+    e = _consts()
+    X, y, ell = o.synthetic_problem(600, 5, seed=3)
+    axes = [np.linspace(0, 1, 6)] * 5                           # 7776 candidates
+    grid = CandidateGrid(axes)
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    full = eng.acquire(fit, grid, outputs=True, chunk=2048)
+    for world in (2, 3, 8):
+        parts, pairs = [], []
+        for r in range(world):
+            b, en = shard_range(grid.size, r, world)
+            res = eng.acquire(fit, grid, b, en, outputs=True, chunk=512)
+            parts.append(res.acq.cpu().numpy())
+            pairs.append((res.best_score, res.best_index))
+        np.testing.assert_array_equal(np.concatenate(parts), full.acq.cpu().numpy())
+        assert reduce_pairs(pairs) == (full.best_score, full.best_index)
+
+
+def test_exact_ties_resolve_to_lowest_flat_index(eng):
+    e = _consts()
+    X = np.array([[0.0, 0.0], [1.0, 1.0]])
+    y = np.array([1.0, 2.0])
+    P = np.full((500, 2), 1e3) + np.arange(500)[:, None]        # k_* underflows to exactly 0 everywhere
+    fit = eng.fit(X, y, np.array([0.5, 0.5]), e.JITTER_POSTERIOR)
+    res = eng.acquire(fit, P, outputs=True)
+    assert np.all(res.mu.cpu().numpy() == 0.0)
+    assert np.all(res.sigma.cpu().numpy() == np.sqrt(e.PRIOR_DIAG))
+    assert res.best_index == 0
+    res = eng.acquire(fit, P, 123, 400)
+    assert res.best_index == 123
+
+
+def test_nan_acquisition_raises_index_error(eng):
+    import torch
+    mu = torch.tensor([0.0, float("nan"), 1.0], dtype=torch.float64).cuda()
+    sig = torch.ones(3, dtype=torch.float64).cuda()
+    with pytest.raises(IndexError):
+        eng.score_argmax(mu, sig)
+
+
+# ------------------------------------------------------------------ K3
+@pytest.mark.parametrize("n,d", [(2, 1), (7, 2), (21, 2), (64, 5)])
+def test_nlml_batched_small_matches_literal_reference_formula(eng, n, d):
+    rng = np.random.default_rng(n)
+    X, y = rng.random((n, d)) * 10, rng.uniform(1e7, 1e9, n)
+    ells = 0.5 + 5 * rng.random((40, d))
+    got, grad = eng.nlml_batched(X, y, ells, want_grad=True)
+    got, grad = got.cpu().numpy(), grad.cpu().numpy()
+    for r in range(len(ells)):
+        lit = o.nlml(X, y, ells[r], stable=False)
+        if np.isfinite(lit):
+            assert abs(got[r] - lit) <= RTOL * abs(lit)
+        gref = o.nlml_grad(X, y, ells[r])
+        np.testing.assert_allclose(grad[r], gref, rtol=1e-6, atol=1e-6 * np.abs(gref).max())
+
+
+@pytest.mark.parametrize("n,d,R", [(100, 3, 5), (512, 8, 6), (130, 2, 3)])
+def test_nlml_batched_large_matches_oracle(eng, n, d, R):
+    rng = np.random.default_rng(n + R)
+    X, y, _ = o.synthetic_problem(n, d, seed=n)
+    ells = np.exp(rng.uniform(np.log(0.2), np.log(1.0), (R, d)))
+    got, grad = eng.nlml_batched(X, y, ells, want_grad=True)
+    got, grad = got.cpu().numpy(), grad.cpu().numpy()
+    for r in range(R):
+        ref = o.nlml(X, y, ells[r], stable=True)
+        assert abs(got[r] - ref) <= RTOL * abs(ref), (r, got[r], ref)
+        gref = o.nlml_grad(X, y, ells[r])
+        np.testing.assert_allclose(grad[r], gref, rtol=1e-6, atol=1e-7 * np.abs(gref).max())
+    only = eng.nlml_batched(X, y, ells).cpu().numpy()
+    np.testing.assert_array_equal(only, got)
+
+
+# ------------------------------------------------------------------ drop-in class on the reference's own cases
+def _length_scales(g):
+    return np.array([g["ls0"], g["ls1"]]) if "ls1" in g else g["ls0"]
+
+
+@pytest.mark.parametrize("name", golden_names("native"))
+def test_point_selector_dropin_matches_reference(name):
+    from bayesian_optimisation_b200.point_selector import PointSelector
+    g = load_golden(name)
+    ps = PointSelector()
+    ps.name, ps.iteration = "golden", 1
+    ps.measured_pts, ps.measured_vals = g["X"].copy(), g["y"].copy()
+    ps.feature_domain = list(g["feature_domain"])
+    ps.predicted_pts = g["P"].copy()
+    ps.length_scales = _length_scales(g)
+    ps.update_surrogate()
+    idx = ps.lower_confidence_bound()
+    assert isinstance(ps.measured_pts, list) and isinstance(ps.measured_vals, list)     # point_selector.py:101-102
+    assert np.asarray(ps.kernel_params).shape == g["kernel_params"].shape
+    np.testing.assert_array_equal(ps.kernel_params, g["kernel_params"])
+    scale = np.abs(g["mean_func"]).max()
+    np.testing.assert_allclose(ps.mean_func, g["mean_func"], rtol=RTOL, atol=RTOL * scale)
+    assert_var_close(ps.cov_func ** 2, g["cov_func"] ** 2)
+    np.testing.assert_array_equal(idx, g["index"])
+    assert idx.dtype == np.int64 and ps.acq_func_eval.shape == g["acq"].shape
+    np.testing.assert_array_equal(ps.acq_func_eval, 4 * ps.cov_func - ps.mean_func)
+
+
+def test_point_selector_inspection_matrices():
+    from bayesian_optimisation_b200.point_selector import PointSelector
+    g = load_golden("native1d_tr_m8")
+    ps = PointSelector()
+    ps.measured_pts, ps.measured_vals = g["X"], g["y"]
+    ps.feature_domain, ps.predicted_pts, ps.length_scales = [50], g["P"], g["ls0"]
+    ps.update_surrogate()
+    ell = np.asarray(ps.kernel_params).reshape(-1)
+    np.testing.assert_allclose(ps.cov_meas, o.kernel_rbf(g["X"], g["X"], ell) + 1e-6 * np.eye(8), rtol=1e-13)
+    np.testing.assert_allclose(ps.cov_meas_pred, o.kernel_rbf(g["X"], g["P"], ell).T, rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(ps.cov_pred, o.kernel_rbf(g["P"], g["P"], ell) + 1e-6 * np.eye(50), rtol=1e-13, atol=1e-300)
