@@ -45,6 +45,8 @@ SIGNATURES = {
     "bogp_set_stream": (_i32, [_vp, _vp]),
     "bogp_sm_count": (_i32, [_vp]),
     "bogp_launch_count": (_i64, [_vp]),
+    "bogp_profile": (_i32, [_vp, _i32]),
+    "bogp_profile_read": (_i32, [_vp, _i32, C.POINTER(_dbl), C.POINTER(_i64)]),
     "bogp_kernel_matrix": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _dbl, _vp, _i64]),
     "bogp_fit_workspace_bytes": (_sz, [_i64, _i32]),
     "bogp_fit_create": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _dbl, _vp, _sz, C.POINTER(_vp), C.POINTER(_dbl)]),

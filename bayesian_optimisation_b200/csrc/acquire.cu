@@ -376,17 +376,17 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
         const int64_t cur = (c_end - c0 < S) ? (c_end - c0) : S;
         const int nct = (int)((cur + kAcqBN - 1) / kAcqBN);
         PanelArgs pa{cd, fit_xpad(fit), fit_inv_ell2(fit), fit_alpha(fit), panel, mupart, c0, c_end, S, (int)fit_n(fit), (int)n_pad, dim};
-        panel_kernel<<<dim3(nct, nI), 256, 0, st>>>(pa); BOGP_LAUNCH_CHECK(ctx);
+        BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_kernel<<<dim3(nct, nI), 256, 0, st>>>(pa))); BOGP_LAUNCH_CHECK(ctx);
         TriArgs ta{fit_wp(fit), panel, qpart, nI, nct, (int)n_pad, S};
-        trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta); BOGP_LAUNCH_CHECK(ctx);
+        BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta))); BOGP_LAUNCH_CHECK(ctx);
         const int nfb = (int)((cur + 255) / 256);
         if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }
         const int64_t o = c0 - c_begin;
         FinalArgs fa{qpart, mupart, d_mu_out ? d_mu_out + o : nullptr, d_sigma_out ? d_sigma_out + o : nullptr,
                      d_acq_out ? d_acq_out + o : nullptr, ctx->d_block_score, ctx->d_block_index, nan_flag,
                      c0, cur, S, nI, kind, explore, f_best, prior_diag};
-        finalize_kernel<<<nfb, 256, 0, st>>>(fa); BOGP_LAUNCH_CHECK(ctx);
-        merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti); BOGP_LAUNCH_CHECK(ctx);
+        BOGP_PROFILED(ctx, BOGP_PROF_FINALIZE, (finalize_kernel<<<nfb, 256, 0, st>>>(fa))); BOGP_LAUNCH_CHECK(ctx);
+        BOGP_PROFILED(ctx, BOGP_PROF_MERGE, (merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti))); BOGP_LAUNCH_CHECK(ctx);
     }
     if (h_best_score || h_best_index) {
         double hs; long long hi; int hn;

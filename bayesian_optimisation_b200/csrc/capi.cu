@@ -41,12 +41,29 @@ extern "C" int bogp_create(int device, bogp_ctx** out) {
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_block_index, kMaxReduceBlocks * sizeof(long long)));
     BOGP_CUDA_CHECK(cudaMemset(c->d_scalars, 0, 64 * sizeof(double)));
     BOGP_CUDA_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+    BOGP_CUDA_CHECK(cudaEventCreate(&c->ev[0]));
+    BOGP_CUDA_CHECK(cudaEventCreate(&c->ev[1]));
     *out = c;
+    return BOGP_OK;
+}
+
+extern "C" int bogp_profile(bogp_ctx* ctx, int enable) {
+    if (!ctx) { set_error("bogp_profile: null context"); return BOGP_ERR_BAD_ARG; }
+    ctx->profile = enable ? 1 : 0;
+    for (int i = 0; i < 8; i++) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; }
+    return BOGP_OK;
+}
+
+extern "C" int bogp_profile_read(const bogp_ctx* ctx, int kernel_id, double* ms_total, int64_t* launches) {
+    if (!ctx || kernel_id < 0 || kernel_id >= 8) { set_error("bogp_profile_read: bad argument"); return BOGP_ERR_BAD_ARG; }
+    if (ms_total) *ms_total = ctx->prof_ms[kernel_id];
+    if (launches) *launches = ctx->prof_n[kernel_id];
     return BOGP_OK;
 }
 
 extern "C" void bogp_destroy(bogp_ctx* ctx) {
     if (!ctx) return;
+    cudaEventDestroy(ctx->ev[0]); cudaEventDestroy(ctx->ev[1]);
     cudaFree(ctx->d_scalars); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_score); cudaFree(ctx->d_block_index);
     delete ctx;
 }

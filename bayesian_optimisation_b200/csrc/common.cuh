@@ -33,6 +33,25 @@ void set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
+// kernel ids for bogp_profile_read
+#define BOGP_PROF_PANEL    0
+#define BOGP_PROF_TRIGEMM  1
+#define BOGP_PROF_FINALIZE 2
+#define BOGP_PROF_MERGE    3
+
+// Time one launch with CUDA events on the launching stream when profiling is on (serialises the stream).
+#define BOGP_PROFILED(ctx, id, launch)                                                    \
+    do {                                                                                  \
+        if ((ctx)->profile) cudaEventRecord((ctx)->ev[0], (ctx)->stream);                 \
+        launch;                                                                           \
+        if ((ctx)->profile) {                                                             \
+            cudaEventRecord((ctx)->ev[1], (ctx)->stream);                                 \
+            cudaEventSynchronize((ctx)->ev[1]);                                           \
+            float _ms = 0.f; cudaEventElapsedTime(&_ms, (ctx)->ev[0], (ctx)->ev[1]);      \
+            (ctx)->prof_ms[id] += _ms; (ctx)->prof_n[id]++;                               \
+        }                                                                                 \
+    } while (0)
+
 #define BOGP_LAUNCH_CHECK(ctx)                                                            \
     do {                                                                                  \
         (ctx)->launches++;                                                                \
@@ -52,6 +71,11 @@ struct bogp_ctx {
     double*      d_block_score; // kMaxBlocks
     long long*   d_block_index; // kMaxBlocks
     double*      h_pinned;      // 64 doubles pinned host staging
+    // optional per-kernel timing of the acquisition sweep (bogp_profile): CUDA events on the launching stream
+    int          profile;
+    cudaEvent_t  ev[2];
+    double       prof_ms[8];
+    int64_t      prof_n[8];
 };
 
 namespace bogp {

@@ -127,6 +127,18 @@ class GPEngine:
     def sm_count(self) -> int:
         return int(self.lib.bogp_sm_count(self._ctx))
 
+    def profile(self, enable: bool):
+        """Per-kernel CUDA-event timing of the acquisition sweep (measurement aid; serialises the stream)."""
+        _lib.check(self.lib.bogp_profile(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        out = {}
+        for kid, name in enumerate(["panel", "trigemm", "finalize", "merge"]):
+            ms, n = C.c_double(), C.c_int64()
+            _lib.check(self.lib.bogp_profile_read(self._ctx, kid, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, int(n.value))
+        return out
+
     def close(self):
         if getattr(self, "_ctx", None):
             self.lib.bogp_destroy(self._ctx)

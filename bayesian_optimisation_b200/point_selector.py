@@ -75,6 +75,13 @@ class PointSelector():
             self._engine = _engine.default_engine()
         return self._engine
 
+    def _ell_vector(self, dim):
+        """kernel_params as a length-`dim` vector.  A single length scale broadcasts over all
+        features exactly as numpy broadcasting does in point_selector.py:188 (that is what the
+        reference computes when a 1-D length-scale grid meets d > 1 features)."""
+        ell = np.asarray(self.kernel_params, dtype=np.float64).reshape(-1)
+        return np.full(dim, ell[0]) if (ell.size == 1 and dim > 1) else ell
+
     def _log(self, *a):
         if self.verbose:
             print(*a)
@@ -85,9 +92,9 @@ class PointSelector():
         if val is not None or self.kernel_params is None:
             return val
         eng = self._eng()
-        ell = np.asarray(self.kernel_params, dtype=np.float64).reshape(-1)
         X = np.asarray(self.measured_pts, dtype=np.float64)
         P = np.asarray(self.predicted_pts, dtype=np.float64)
+        ell = self._ell_vector(X.shape[1])
         if which == "cov_pred":
             val = eng.kernel_matrix(P, P, ell, PRIOR_DIAG - 1.0).cpu().numpy()
         elif which == "cov_meas":
@@ -120,7 +127,7 @@ class PointSelector():
                 self.kernel_params = np.array([self.length_scales[len(self.length_scales) // 2]])
 
         eng = self._eng()
-        ell = np.asarray(self.kernel_params, dtype=np.float64).reshape(-1)
+        ell = self._ell_vector(self.measured_pts.shape[1])
         fit = eng.fit(self.measured_pts, self.measured_vals, ell, JITTER_POSTERIOR)
         try:
             if self.predicted_axes is not None:
@@ -160,7 +167,7 @@ class PointSelector():
                 _plot_utils.plot_ARD_LL(nlogml, self.kernel_params, self.length_scales, self.name, self.iteration)
         else:
             grid = np.asarray(self.length_scales, dtype=np.float64).reshape(-1)
-            table = eng.nlml_batched(X, y, grid.reshape(-1, 1), JITTER_LML).cpu().numpy()
+            table = eng.nlml_batched(X, y, np.repeat(grid.reshape(-1, 1), X.shape[1], axis=1), JITTER_LML).cpu().numpy()
             nlogml = table.astype(np.float32)                                          # :150
             min_idx = np.argwhere(nlogml == np.amin(nlogml))[0]                        # :159
             self.kernel_params = np.array([grid[min_idx]])                             # shape (1, 1), :161
@@ -173,7 +180,7 @@ class PointSelector():
         """point_selector.py:166-195 (jitter iff the shapes are equal)."""
         x1 = np.asarray(x1, dtype=np.float64)
         x2 = np.asarray(x2, dtype=np.float64)
-        ell = np.asarray(self.kernel_params, dtype=np.float64).reshape(-1)
+        ell = self._ell_vector(x1.shape[1])
         return self._eng().kernel_matrix(x1, x2, ell, JITTER_LML if x1.shape == x2.shape else 0.0).cpu().numpy()
 
     def _device_mu_sigma(self):

@@ -51,6 +51,11 @@ int  bogp_set_stream(bogp_ctx* ctx, void* cuda_stream);
 int  bogp_sm_count(const bogp_ctx* ctx);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t bogp_launch_count(const bogp_ctx* ctx);
+/* Measurement aid: when enabled, each kernel of the acquisition sweep is bracketed by CUDA
+ * events on the launching stream (this serialises the stream; never enable it inside a timed
+ * region).  kernel_id: 0 panel, 1 tri-GEMM, 2 finalize, 3 merge.                            */
+int bogp_profile(bogp_ctx* ctx, int enable);
+int bogp_profile_read(const bogp_ctx* ctx, int kernel_id, double* ms_total, int64_t* launches);
 
 /* ---- K1: ARD squared-exponential Gram matrix ------------------- point_selector.py:166-195
  * K[i,j] = exp(-0.5 * sum_k (a_ik-b_jk)^2 / ell_k^2) (+ jitter where i == j), row-major,
@@ -80,8 +85,8 @@ const double* bogp_fit_alpha(const bogp_fit* fit);    /* n_pad doubles          
 double        bogp_fit_logdet(const bogp_fit* fit);   /* host value (synchronises)                              */
 
 /* stand-alone blocked Cholesky of a row-major lower-stored n x n matrix, in place
- * (n multiple of 64).  d_linv (n x n, may be NULL) receives the inverse of the 64x64
- * diagonal blocks on its diagonal blocks.  d_logdet: one double.  d_info: one int
+ * (n multiple of 64).  d_linv (n x n, zero-initialised, required) receives the inverse of the
+ * 64x64 diagonal blocks on its diagonal blocks (the panel solve multiplies with them).  d_logdet: one double.  d_info: one int
  * (0, or 1-based index of the first bad pivot).                                          */
 int bogp_cholesky(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, double* d_linv,
                   double* d_logdet, int* d_info);
