@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include "fit.cuh"
+#include "chol_diag.cuh"
 
 namespace bogp {
 
@@ -103,110 +104,54 @@ int launch_inv_ell2(bogp_ctx* ctx, const double* d_ell, double* d_out, int64_t c
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 diagonal block: 64x64 Cholesky + inverse of the factor, one CTA per matrix of the batch.
-// The pivot is broadcast through shared memory; the 4 partial sums of each inverse entry are
-// combined with warp shuffles.
-// ------------------------------------------------------------------------------------------------
-struct DiagArgs {
-    double* a; int64_t lda; int64_t strideA;
-    double* w; int64_t ldw; int64_t strideW;
-    double* logdet; int* info; int kblk;
-};
-
-__global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
-    constexpr int NB = kDiagNB, LD = NB + 1;
-    extern __shared__ __align__(16) double diag_smem[];
-    double* a = diag_smem;
-    double* x = a + NB * LD;
-    double* dg = x + NB * LD;
-    const int tid = threadIdx.x;
-    double* A = g.a + blockIdx.x * g.strideA + (int64_t)g.kblk * NB * (g.lda + 1);
-    for (int i = tid; i < NB * NB; i += 256) {
-        int r = i / NB, c = i % NB;
-        a[r * LD + c] = (c <= r) ? A[(int64_t)r * g.lda + c] : 0.0;
-        x[r * LD + c] = 0.0;
-    }
-    bool bad = false;
-    for (int j = 0; j < NB; j++) {
-        __syncthreads();
-        const double ajj = a[j * LD + j];
-        if (!(ajj > 0.0) || isinf(ajj)) bad = true;
-        const double d = sqrt(ajj);
-        if (tid == j) dg[j] = d;
-        if (tid > j && tid < NB) a[tid * LD + j] = a[tid * LD + j] / d;
-        __syncthreads();
-        const int rem = NB - 1 - j;
-        for (int idx = tid; idx < rem * rem; idx += 256) {
-            int i = j + 1 + idx / rem, l = j + 1 + idx % rem;
-            if (l <= i) a[i * LD + l] -= a[i * LD + j] * a[l * LD + j];
-        }
-        if (bad && tid == 0) { atomicCAS(g.info + blockIdx.x, 0, g.kblk * NB + j + 1); }
-        bad = false;
-    }
-    __syncthreads();
-    if (tid < NB) a[tid * LD + tid] = dg[tid];
-    __syncthreads();
-    // X = L^-1, column c by forward substitution; 4 lanes share one column.
-    {
-        const int c = tid >> 2, q = tid & 3;
-        if (q == 0) x[c * LD + c] = 1.0 / dg[c];
-        __syncwarp();
-        for (int i = 1; i < NB; i++) {
-            double s = 0.0;
-            if (i > c) for (int k = c + q; k < i; k += 4) s += a[i * LD + k] * x[k * LD + c];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (i > c && q == 0) x[i * LD + c] = -s / dg[i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    double* W = g.w ? g.w + blockIdx.x * g.strideW + (int64_t)g.kblk * NB * (g.ldw + 1) : nullptr;
-    for (int i = tid; i < NB * NB; i += 256) {
-        int r = i / NB, c = i % NB;
-        if (c <= r) A[(int64_t)r * g.lda + c] = a[r * LD + c];
-        if (W) W[(int64_t)r * g.ldw + c] = x[r * LD + c];
-    }
-    if (tid < 32 && g.logdet) {   // fixed-order sum of 2*log(d_j)
-        double s = 0.0;
-        if (tid == 0) { for (int j = 0; j < NB; j++) s += 2.0 * log(dg[j]); g.logdet[blockIdx.x] += s; }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky, batch of `batch` matrices (strides in doubles).
 // ------------------------------------------------------------------------------------------------
 int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
                      int64_t strideW, double* d_logdet, int* d_info, int batch) {
     if (n % kDiagNB != 0) { set_error("cholesky: n=%lld is not a multiple of %d", (long long)n, kDiagNB); return BOGP_ERR_BAD_ARG; }
-    const int nblk = (int)(n / kDiagNB);
-    constexpr size_t kDiagSmem = (size_t)(2 * kDiagNB * (kDiagNB + 1) + kDiagNB) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        BOGP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
-        configured = true;
-    }
-    for (int kb = 0; kb < nblk; kb++) {
-        DiagArgs dg{d_a, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, kb};
-        chol_diag_kernel<<<batch, 256, kDiagSmem, ctx->stream>>>(dg);
-        BOGP_LAUNCH_CHECK(ctx);
-        const int below = (int)(n - (int64_t)(kb + 1) * kDiagNB);
-        if (below <= 0) break;
-        double* panel = d_a + (int64_t)(kb + 1) * kDiagNB * lda + (int64_t)kb * kDiagNB;
-        const double* dinv = d_w + (int64_t)kb * kDiagNB * (ldw + 1);
-        GemmArgs t{};   // panel <- panel * Dinv^T   (in place: one CTA owns complete rows, K fully staged before the stores)
-        t.A = panel; t.lda = lda; t.strideA = strideA;
-        t.B = dinv;  t.ldb = ldw; t.strideB = strideW;
-        t.C = panel; t.ldc = lda; t.strideC = strideA;
-        t.M = below; t.N = kDiagNB; t.K = kDiagNB; t.alpha = 1.0; t.accumulate = 0; t.lower_only = 0;
-        int rc = launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, t, batch);
-        if (rc) return rc;
-        GemmArgs s{};   // trailing -= panel * panel^T   (lower part only)
-        s.A = panel; s.lda = lda; s.strideA = strideA;
-        s.B = panel; s.ldb = lda; s.strideB = strideA;
-        s.C = d_a + (int64_t)(kb + 1) * kDiagNB * (lda + 1); s.ldc = lda; s.strideC = strideA;
-        s.M = below; s.N = below; s.K = kDiagNB; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
-        rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, s, batch);
+    // Two-level right-looking blocking: an outer panel of kOuter columns is factored with
+    // NB=64 steps whose SYRK only touches the panel; the big trailing update then runs once
+    // per outer panel with K = kOuter (16 pipeline k-steps per tile instead of 4).
+    constexpr int kOuter = 256;
+    auto syrk = [&](int64_t row0, int64_t ncols, int64_t pcol0, int K) -> int {
+        // C[row0.., row0..row0+ncols) -= P P^T, P = A[row0.., pcol0..pcol0+K)   (lower part)
+        const int m = (int)(n - row0);
+        if (m <= 0 || ncols <= 0) return BOGP_OK;
+        GemmArgs s{};
+        const double* P = d_a + row0 * lda + pcol0;
+        s.A = P; s.lda = lda; s.strideA = strideA;
+        s.B = P; s.ldb = lda; s.strideB = strideA;
+        s.C = d_a + row0 * (lda + 1); s.ldc = lda; s.strideC = strideA;
+        s.M = m; s.N = (int)ncols; s.K = K; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
+        int rc = BOGP_OK;
+        BOGP_PROFILED(ctx, K == kDiagNB ? 6 : 7, (rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, s, batch)));
+        return rc;
+    };
+    for (int64_t ko = 0; ko < n; ko += kOuter) {
+        const int64_t wpan = (n - ko < kOuter) ? (n - ko) : kOuter;
+        for (int64_t ki = 0; ki < wpan; ki += kDiagNB) {
+            const int64_t k = ko + ki;
+            DiagArgs dg{d_a, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, (int)(k / kDiagNB)};
+            BOGP_PROFILED(ctx, 4, (chol_diag_kernel<<<batch, 256, 0, ctx->stream>>>(dg)));
+            BOGP_LAUNCH_CHECK(ctx);
+            const int below = (int)(n - (k + kDiagNB));
+            if (below <= 0) break;
+            double* panel = d_a + (k + kDiagNB) * lda + k;
+            const double* dinv = d_w + k * (ldw + 1);
+            GemmArgs t{};   // panel <- panel * Dinv^T   (in place: one CTA owns complete rows, K fully staged before the stores)
+            t.A = panel; t.lda = lda; t.strideA = strideA;
+            t.B = dinv;  t.ldb = ldw; t.strideB = strideW;
+            t.C = panel; t.ldc = lda; t.strideC = strideA;
+            t.M = below; t.N = kDiagNB; t.K = kDiagNB; t.alpha = 1.0; t.accumulate = 0; t.lower_only = 0;
+            int rc = BOGP_OK;
+            BOGP_PROFILED(ctx, 5, (rc = launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, t, batch)));
+            if (rc) return rc;
+            // inner update: only the remaining columns of this outer panel
+            rc = syrk(k + kDiagNB, ko + wpan - (k + kDiagNB), k, kDiagNB);
+            if (rc) return rc;
+        }
+        // outer update of everything right of the panel
+        int rc = syrk(ko + wpan, n - (ko + wpan), ko, (int)wpan);
         if (rc) return rc;
     }
     return BOGP_OK;
@@ -293,7 +238,10 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restr
     const int rows = n - c0, per = (rows + 7) / 8;
     const int rb = c0 + sl * per, re = min(n, rb + per);
     double s = 0.0;
-    if (col < n) for (int i = max(rb, col); i < re; i++) s += w[(int64_t)i * ldw + col] * v[i];
+    if (col < n) {
+#pragma unroll 8
+        for (int i = max(rb, col); i < re; i++) s += w[(int64_t)i * ldw + col] * v[i];
+    }
     part[sl][threadIdx.x & 31] = s;
     __syncthreads();
     if (sl == 0 && col < n) {

@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
     const int wm = warp >> 1, wn = warp & 1;
     constexpr int WM = BM / 4, WN = BN / 2, MI = WM / 8, NI = WN / 8;
 
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // row blocks whose k range grows with m are scheduled heaviest-first
+    const int by = (KR == K_LE_M) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int m0 = by * BM, n0 = blockIdx.x * BN;
     if (g.lower_only && n0 > m0 + BM - 1) return;
 
     const int zi = g.inner > 1 ? (int)(blockIdx.z % g.inner) : (g.inner == 1 ? 0 : (int)blockIdx.z);

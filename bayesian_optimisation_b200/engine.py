@@ -133,7 +133,7 @@ class GPEngine:
 
     def profile_read(self):
         out = {}
-        for kid, name in enumerate(["panel", "trigemm", "finalize", "merge"]):
+        for kid, name in enumerate(["panel", "trigemm", "finalize", "merge", "chol_diag", "chol_trsm", "chol_syrk_inner", "chol_syrk_outer"]):
             ms, n = C.c_double(), C.c_int64()
             _lib.check(self.lib.bogp_profile_read(self._ctx, kid, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, int(n.value))
