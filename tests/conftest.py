@@ -41,3 +41,27 @@ def load_golden(name):
     import numpy as np
     with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
         return {k: z[k] for k in z.files}
+
+
+def load_closed_loop():
+    """Calls recorded from the unmodified reference workflow (oracle/make_closed_loop.py)."""
+    import numpy as np
+    g = load_golden("closed_loop")
+    offs = np.concatenate([[0], np.cumsum(g["table_len"])])
+    tables = [g["tables"][offs[i]:offs[i + 1]] for i in range(len(g["table_len"]))]
+    calls, xo, yo = [], 0, 0
+    for c in range(int(g["n_calls"])):
+        M, d = int(g["M"][c]), int(g["d"][c])
+        X = g["X"][xo:xo + M * d].reshape(M, d); xo += M * d
+        y = g["y"][yo:yo + M]; yo += M
+        axes = [tables[i] for i in g["axes_id"][c] if i >= 0]
+        ls = [tables[i] for i in g["ls_id"][c] if i >= 0]
+        mesh = np.meshgrid(*axes, indexing="ij")
+        P = np.stack([m.reshape(-1) for m in mesh], axis=1)
+        kp = g["kp"][c][:d]
+        kp = kp.reshape(1, 1) if g["kp_ndim"][c] == 2 else kp
+        calls.append(dict(X=X, y=y, P=P, axes=axes, feature_domain=[len(a) for a in axes],
+                          length_scales=np.array(ls) if len(ls) == 2 else ls[0], kernel_params=kp,
+                          index=g["index"][c][:d], acq_max=float(g["acq_max"][c]), mu_min=float(g["mu_min"][c]),
+                          sig_max=float(g["sig_max"][c])))
+    return calls

@@ -276,3 +276,32 @@ def test_point_selector_inspection_matrices():
     np.testing.assert_allclose(ps.cov_meas, o.kernel_rbf(g["X"], g["X"], ell) + 1e-6 * np.eye(8), rtol=1e-13)
     np.testing.assert_allclose(ps.cov_meas_pred, o.kernel_rbf(g["X"], g["P"], ell).T, rtol=1e-13, atol=1e-300)
     np.testing.assert_allclose(ps.cov_pred, o.kernel_rbf(g["P"], g["P"], ell) + 1e-6 * np.eye(50), rtol=1e-13, atol=1e-300)
+
+
+def test_point_selector_dropin_replays_the_reference_closed_loop():
+    """all PointSelector calls made by the unmodified select_parameters.py while the
+    unmodified terminate_opto/block/algo.py scripts drive two full algorithm iterations (trace
+    recorded by oracle/make_closed_loop.py).  The drop-in must choose the same length scales and the
+    same next point at every step -- otherwise the workflow would diverge from the reference."""
+    from conftest import load_closed_loop
+    from bayesian_optimisation_b200.point_selector import PointSelector
+    calls = load_closed_loop()
+    for n, c in enumerate(calls):
+        ps = PointSelector()
+        ps.name, ps.iteration = "trace", n
+        ps.measured_pts, ps.measured_vals = c["X"].copy(), c["y"].copy()
+        ps.feature_domain, ps.predicted_pts, ps.length_scales = list(c["feature_domain"]), c["P"], c["length_scales"]
+        ps.update_surrogate()
+        idx = ps.lower_confidence_bound()
+        assert np.asarray(ps.kernel_params).shape == c["kernel_params"].shape, n
+        np.testing.assert_array_equal(ps.kernel_params, c["kernel_params"], err_msg=f"call {n}")
+        np.testing.assert_array_equal(idx, c["index"], err_msg=f"call {n}")
+        assert abs(ps.acq_func_eval.max() - c["acq_max"]) <= 1e-9 * max(1.0, abs(c["acq_max"])), n
+        assert abs(ps.mean_func.min() - c["mu_min"]) <= 1e-9 * max(1.0, abs(c["mu_min"])), n
+        # grid given as axes (never materialised) selects the same point
+        if n % 10 == 0:
+            ps2 = PointSelector()
+            ps2.measured_pts, ps2.measured_vals = c["X"].copy(), c["y"].copy()
+            ps2.feature_domain, ps2.predicted_axes, ps2.length_scales = list(c["feature_domain"]), c["axes"], c["length_scales"]
+            ps2.update_surrogate()
+            np.testing.assert_array_equal(ps2.lower_confidence_bound(), c["index"])

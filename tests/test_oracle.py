@@ -110,3 +110,18 @@ def test_oracle_against_live_reference_random():
         np.testing.assert_allclose(r["mean_func"], ref["mean_func"], rtol=1e-11, atol=1e-9 * np.abs(ref["mean_func"]).max())
         np.testing.assert_array_equal(r["index"], ref["index"])
         assert ref["measured_pts_type"] == "list"
+
+
+def test_oracle_replays_the_reference_closed_loop_trace():
+    """Every 4th PointSelector call of the recorded reference workflow (select_parameters.py +
+    terminate_*.py + synthetic objective): same length scales, same selected index."""
+    from conftest import load_closed_loop
+    calls = load_closed_loop()
+    assert len(calls) > 100 and {len(c["X"]) for c in calls} >= {1, 2, 5}
+    assert {c["X"].shape[1] for c in calls} == {1, 2}
+    for c in calls[::4]:
+        r = o.select_next(c["X"], c["y"], c["P"], c["feature_domain"], c["length_scales"])
+        assert np.asarray(r["kernel_params"]).shape == c["kernel_params"].shape
+        np.testing.assert_array_equal(r["kernel_params"], c["kernel_params"])
+        np.testing.assert_array_equal(r["index"], c["index"])
+        assert abs(r["acq"].max() - c["acq_max"]) <= 1e-9 * max(1.0, abs(c["acq_max"]))
