@@ -20,6 +20,8 @@ BOGP_ERR_WORKSPACE = -5
 BOGP_MAX_DIM = 16
 ACQ_LCB = 0
 ACQ_EI = 1
+PATH_FP64_DMMA = 0
+PATH_INT8_TCGEN05 = 1
 
 
 class BogpError(RuntimeError):
@@ -45,6 +47,8 @@ SIGNATURES = {
     "bogp_set_stream": (_i32, [_vp, _vp]),
     "bogp_sm_count": (_i32, [_vp]),
     "bogp_launch_count": (_i64, [_vp]),
+    "bogp_set_acquire_path": (_i32, [_vp, _i32]),
+    "bogp_get_acquire_path": (_i32, [_vp]),
     "bogp_profile": (_i32, [_vp, _i32]),
     "bogp_profile_read": (_i32, [_vp, _i32, C.POINTER(_dbl), C.POINTER(_i64)]),
     "bogp_kernel_matrix": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _dbl, _vp, _i64]),

@@ -221,7 +221,7 @@ struct FinalArgs {
     const double* qpart; const double* mupart;
     double* mu_out; double* sigma_out; double* acq_out;   // already offset to this chunk (or null)
     double* block_score; long long* block_index; int* nan_flag;
-    int64_t c0, cur, S; int nI; int kind; double explore, f_best, prior;
+    int64_t c0, cur, S; int nIq, nImu; int kind; double explore, f_best, prior;
 };
 
 __device__ __forceinline__ double acquisition_value(int kind, double mu, double sigma, double explore, double f_best) {
@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs f) {
     double score = -INFINITY; long long idx = kNoIndex;
     if (cl < f.cur) {
         double q = 0.0, mu = 0.0;
-        for (int b = 0; b < f.nI; b++) { q += f.qpart[(int64_t)b * f.S + cl]; mu += f.mupart[(int64_t)b * f.S + cl]; }
+        for (int b = 0; b < f.nIq; b++) q += f.qpart[(int64_t)b * f.S + cl];
+        for (int b = 0; b < f.nImu; b++) mu += f.mupart[(int64_t)b * f.S + cl];
         const double var = f.prior - q;
         const double sigma = sqrt(fabs(var));                   // np.sqrt(np.abs(.)), point_selector.py:98
         score = acquisition_value(f.kind, mu, sigma, f.explore, f.f_best);
@@ -307,14 +308,19 @@ __global__ void init_best_kernel(double* best, long long* besti, int* nan_flag) 
     best[0] = -INFINITY; besti[0] = kNoIndex; nan_flag[0] = 0;
 }
 
-struct AcqLayout { size_t panel, qpart, mupart, axes_unused, total; int64_t S; };
+// Workspace of one chunk of S candidates.  The layout is sized for the larger of the two tensor
+// paths (FP64: 8 B per panel entry, 256-row blocks; INT8: 7 B per entry, 128-row blocks) so that a
+// workspace is valid whichever path is selected.
+struct AcqLayout { size_t panel, qpart, mupart, total; int64_t S; };
+static size_t acq_bytes_per_candidate(int64_t n_pad) {
+    return (size_t)n_pad * 8 + (size_t)(n_pad / 128) * 8 + (size_t)(n_pad / kAcqBM) * 8;
+}
 static AcqLayout acq_layout(int64_t n_pad, int64_t max_chunk) {
     AcqLayout l{}; size_t off = 0;
     int64_t S = (max_chunk + kAcqBN - 1) / kAcqBN * kAcqBN;
     if (S < kAcqBN) S = kAcqBN;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
-    const int64_t nI = n_pad / kAcqBM;
-    l.panel = take((size_t)n_pad * S * 8); l.qpart = take((size_t)nI * S * 8); l.mupart = take((size_t)nI * S * 8);
+    l.panel = take((size_t)n_pad * S * 8); l.qpart = take((size_t)(n_pad / 128) * S * 8); l.mupart = take((size_t)(n_pad / kAcqBM) * S * 8);
     l.total = off; l.S = S;
     return l;
 }
@@ -352,7 +358,7 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
         if (prod != cand->c_total) { set_error("bogp_acquire: grid has %lld points, c_total says %lld", (long long)prod, (long long)cand->c_total); return BOGP_ERR_BAD_ARG; }
     }
     // chunk capacity from the workspace size
-    const size_t per_cand = (size_t)(n_pad + 2 * nI) * 8;
+    const size_t per_cand = acq_bytes_per_candidate(n_pad);
     int64_t S = (int64_t)(workspace_bytes / per_cand) / kAcqBN * kAcqBN;
     if (S < kAcqBN) { set_error("bogp_acquire: workspace too small"); return BOGP_ERR_WORKSPACE; }
     if (S > (int64_t)kMaxReduceBlocks * 256) S = (int64_t)kMaxReduceBlocks * 256;
@@ -372,19 +378,35 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
     int* nan_flag = ctx->d_flags;
     init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
 
+    const bool use_i8 = ctx->acquire_path == BOGP_PATH_INT8_TCGEN05;
     for (int64_t c0 = c_begin; c0 < c_end; c0 += S) {
         const int64_t cur = (c_end - c0 < S) ? (c_end - c0) : S;
         const int nct = (int)((cur + kAcqBN - 1) / kAcqBN);
-        PanelArgs pa{cd, fit_xpad(fit), fit_inv_ell2(fit), fit_alpha(fit), panel, mupart, c0, c_end, S, (int)fit_n(fit), (int)n_pad, dim};
-        BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_kernel<<<dim3(nct, nI), 256, 0, st>>>(pa))); BOGP_LAUNCH_CHECK(ctx);
-        TriArgs ta{fit_wp(fit), panel, qpart, nI, nct, (int)n_pad, S};
-        BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta))); BOGP_LAUNCH_CHECK(ctx);
+        int nIq;
+        if (use_i8) {
+            AcqChunk a{};
+            a.points = cd.points; a.axes = cd.axes; a.cross_jitter = cd.cross_jitter;
+            for (int k = 0; k < BOGP_MAX_DIM; k++) { a.len[k] = cd.len[k]; a.off[k] = cd.off[k]; }
+            a.x_pad = fit_xpad(fit); a.inv_ell2 = fit_inv_ell2(fit); a.alpha = fit_alpha(fit);
+            a.wp = fit_wp(fit); a.wq = fit_wq(fit); a.wscale = fit_wscale(fit);
+            a.panel = panel; a.qpart = qpart; a.mupart = mupart;
+            a.c0 = c0; a.c_end = c_end; a.cur = cur; a.S = S; a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
+            int rc = launch_acquire_chunk_i8(ctx, a);
+            if (rc) return rc;
+            nIq = (int)(n_pad / 128);
+        } else {
+            PanelArgs pa{cd, fit_xpad(fit), fit_inv_ell2(fit), fit_alpha(fit), panel, mupart, c0, c_end, S, (int)fit_n(fit), (int)n_pad, dim};
+            BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_kernel<<<dim3(nct, nI), 256, 0, st>>>(pa))); BOGP_LAUNCH_CHECK(ctx);
+            TriArgs ta{fit_wp(fit), panel, qpart, nI, nct, (int)n_pad, S};
+            BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta))); BOGP_LAUNCH_CHECK(ctx);
+            nIq = nI;
+        }
         const int nfb = (int)((cur + 255) / 256);
         if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }
         const int64_t o = c0 - c_begin;
         FinalArgs fa{qpart, mupart, d_mu_out ? d_mu_out + o : nullptr, d_sigma_out ? d_sigma_out + o : nullptr,
                      d_acq_out ? d_acq_out + o : nullptr, ctx->d_block_score, ctx->d_block_index, nan_flag,
-                     c0, cur, S, nI, kind, explore, f_best, prior_diag};
+                     c0, cur, S, nIq, nI, kind, explore, f_best, prior_diag};
         BOGP_PROFILED(ctx, BOGP_PROF_FINALIZE, (finalize_kernel<<<nfb, 256, 0, st>>>(fa))); BOGP_LAUNCH_CHECK(ctx);
         BOGP_PROFILED(ctx, BOGP_PROF_MERGE, (merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti))); BOGP_LAUNCH_CHECK(ctx);
     }

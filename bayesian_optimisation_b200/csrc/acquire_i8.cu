@@ -1,0 +1,394 @@
+// K4 on the 5th-generation tensor cores: V = W k_* computed EXACTLY in integer arithmetic
+// (Ozaki-style error-free splitting) with tcgen05.mma kind::i8 and TMEM accumulators.
+//
+// Why: on B200 the FP64 tensor path (DMMA) shares the FP64 pipe and tops out at 37 TFLOP/s
+// (profiles/r01_dmma_bench.txt); the DMMA acquisition kernel already sits at 92-97 % of that.
+// The int8 tensor pipe is ~120x wider, so fp64-exact products are cheaper as sliced integers:
+//
+//   W[i,j]  = 2^{e_i}  * sum_p a_p[i,j] 2^{-7-8p}      a_p in [-128,127]  (7 balanced base-256 digits,
+//   k[j,c]  = 2^{1}    * sum_q b_q[j,c] 2^{-7-8q}      b_q in [-128,127]   fixed point with 55 fraction bits)
+//   V[i,c]  = 2^{e_i+1-14} * sum_t 2^{-8t} S_t[i,c],   S_t = sum_{p+q=t} sum_j a_p[i,j] b_q[j,c]   (int32, exact)
+//
+// Levels t = 0..7 are kept (34 digit pairs); the dropped levels t >= 8 are below 2^-50 of the
+// row scale in the worst case -- smaller than the rounding error of an fp64 dot product of the
+// same length.  |S_t| <= 7 * K * 2^14 < 2^31 for K <= 16384, so int32 accumulation never overflows.
+// Because the integer sums are exact, V does not depend on any summation order: the result is
+// bit-reproducible across tiles, chunks and GPUs by construction.
+//
+// Kernel structure (one CTA = 128 rows of W x 64 candidates, 192 threads):
+//   warp 0   : bulk-TMA producer  (W digit tile 28 KB + panel digit tile 14 KB per K=32 stage, mbarrier ring)
+//   warp 1   : tcgen05.mma issuer (11 MMAs per stage: slice p of W against slices 0..min(6,7-p) of the
+//              panel concatenated along N, landing on TMEM columns 64(p+q)..: the 8 levels fill all 512 columns)
+//   warps 2-5: epilogue -- tcgen05.ld the 8 int32 levels, Horner-combine them in fp64, scale by the row
+//              exponent, square and reduce over the 128 rows (warp shuffles + shared memory).
+#include "common.cuh"
+#include "fit.cuh"
+
+namespace bogp {
+
+constexpr int kI8Slices   = 7;
+constexpr int kI8BM       = 128;                 // rows of W per CTA (UMMA M)
+constexpr int kI8BN       = 64;                  // candidates per CTA
+constexpr int kI8KB       = 32;                  // k per stage (one UMMA K for 8-bit operands)
+constexpr int kI8ATile    = kI8Slices * kI8BM * kI8KB;   // 28672 B
+constexpr int kI8BTile    = kI8Slices * kI8BN * kI8KB;   // 14336 B
+constexpr int kI8Stage    = kI8ATile + kI8BTile;         // 43008 B
+constexpr int kI8Stages   = 4;
+constexpr size_t kI8Smem  = (size_t)kI8Stages * kI8Stage + 256 + 4 * kI8BN * 8;
+
+// ------------------------------------------------------------------------------------------------
+// digit extraction: fx = sum_m d_m 256^m with d_m in [-128,127]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void balanced_digits(long long fx, int (&d)[kI8Slices]) {
+#pragma unroll
+    for (int m = 0; m < kI8Slices; m++) {
+        const int v = (int)(signed char)(fx & 0xFF);
+        d[m] = v;
+        fx = (fx - v) >> 8;
+    }
+}
+
+// per-row exponent of W: |W[i,j]| * 2^-e_i < 1/2   (one warp per row)
+__global__ void __launch_bounds__(256) row_exp_kernel(const double* __restrict__ w, int64_t ldw, int n, int* __restrict__ wexp,
+                                                      double* __restrict__ wscale) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double m = 0.0;
+    for (int j = lane; j <= row; j += 32) m = fmax(m, fabs(w[(int64_t)row * ldw + j]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        const int e = (m > 0.0 ? ilogb(m) : 0) + 2;
+        wexp[row] = e;
+        wscale[row] = ldexp(1.0, e + 1 - 14);      // 2^{e_i} (W) * 2^{1} (panel) * 2^{-7-7}
+    }
+}
+
+// W (row-major, lower) -> digit tiles.  Tile (ib, kt): rows [128 ib, +128) x k [32 kt, +32), kt < 4 (ib+1);
+// layout [slice p][k chunk of 16][row][16 B] so that each slice is a K-major UMMA operand with
+// LBO = 2048 B (next k chunk) and SBO = 128 B (next 8 rows), and a whole tile is one bulk copy.
+__global__ void __launch_bounds__(256) slice_w_kernel(const double* __restrict__ w, int64_t ldw, const int* __restrict__ wexp,
+                                                      uint8_t* __restrict__ wq) {
+    const int ib = blockIdx.y, kt = blockIdx.x;
+    if (kt >= (ib + 1) * (kI8BM / kI8KB)) return;
+    const int64_t tile = (int64_t)ib * (ib + 1) / 2 * (kI8BM / kI8KB) + kt;
+    const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+    const int row = ib * kI8BM + r;
+    const double* src = w + (int64_t)row * ldw + kt * kI8KB + h * 16;
+    const int sh = 55 - wexp[row];
+    uint32_t pk[kI8Slices][4];
+#pragma unroll
+    for (int p = 0; p < kI8Slices; p++) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        int d[kI8Slices];
+        balanced_digits(__double2ll_rn(ldexp(src[e], sh)), d);
+#pragma unroll
+        for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
+    }
+    uint8_t* dst = wq + tile * kI8ATile + h * (kI8BM * 16) + r * 16;
+#pragma unroll
+    for (int p = 0; p < kI8Slices; p++)
+        *reinterpret_cast<uint4*>(dst + p * (kI8BM * kI8KB)) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// panel: k_*[j, c] as digits + partial posterior means.  grid (ceil(cur/64), n_pad/256), 256 threads.
+// Thread = (candidate, 16 consecutive j): 16-byte digit vectors are written per slice; tile layout
+// per (candidate tile, k tile of 32): [k chunk of 16][slice q][candidate][16 B]  (N index = 64 q + cand).
+// ------------------------------------------------------------------------------------------------
+struct CandDescI8 {
+    const double* points; const double* axes;
+    int len[BOGP_MAX_DIM]; int off[BOGP_MAX_DIM];
+    double cross_jitter;
+};
+struct PanelI8Args {
+    CandDescI8 cand;
+    const double* x_pad; const double* inv_ell2; const double* alpha;
+    uint8_t* panel; double* mupart;
+    int64_t c0, c_end, S;
+    int n, n_pad, dim;
+};
+
+__global__ void __launch_bounds__(256) panel_i8_kernel(PanelI8Args p) {
+    __shared__ __align__(128) double ps_raw[kI8BN * BOGP_MAX_DIM];
+    __shared__ double xs[BOGP_MAX_DIM][kAcqBM + 1];
+    __shared__ double al[kAcqBM];
+    __shared__ double sl[BOGP_MAX_DIM];
+    __shared__ double mured[4][kI8BN];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int ct = blockIdx.x, jb = blockIdx.y;
+    const int64_t cbase = p.c0 + (int64_t)ct * kI8BN;
+    const int dim = p.dim;
+    const bool explicit_mode = p.cand.points != nullptr;
+    const int64_t remain = p.c_end - cbase;
+    const int nvalid = remain >= kI8BN ? kI8BN : (int)remain;
+    bool used_tma = false;
+    if (explicit_mode) {
+        const double* src = p.cand.points + cbase * dim;
+        const uint32_t bytes = (uint32_t)nvalid * dim * 8;
+        if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // bulk-TMA staging of the candidate block
+            used_tma = true;
+            if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+            __syncthreads();
+            if (tid == 0) { mbar_expect_tx(&bar, bytes); bulk_g2s(ps_raw, src, bytes, &bar); }
+        }
+    }
+    for (int i = tid; i < kAcqBM * dim; i += 256) {
+        int r = i / dim, k = i % dim;
+        xs[k][r] = p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k];
+    }
+    al[tid] = p.alpha[jb * kAcqBM + tid];
+    if (tid < dim) sl[tid] = p.inv_ell2[tid];
+    if (explicit_mode) {
+        if (used_tma) mbar_wait(&bar, 0);
+        else for (int i = tid; i < nvalid * dim; i += 256) ps_raw[i] = p.cand.points[cbase * dim + i];
+    } else if (tid < nvalid) {
+        int64_t f = cbase + tid;
+        for (int k = dim - 1; k >= 0; k--) {
+            const int64_t q = f / p.cand.len[k];
+            ps_raw[tid * dim + k] = p.cand.axes[p.cand.off[k] + (int)(f - q * p.cand.len[k])];
+            f = q;
+        }
+    }
+    __syncthreads();
+
+    const int nl = tid & 63;                       // candidate within the tile
+    const int ncl = nl < nvalid ? nl : nvalid - 1;
+    double pc[BOGP_MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < BOGP_MAX_DIM; k++) pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0;
+    const int64_t cglob = cbase + nl;
+    double mu = 0.0;      // this thread's 4 row groups, ascending
+    // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
+    for (int g = tid >> 6; g < kAcqBM / 16; g += 4) {
+        uint32_t pk[kI8Slices][4];
+#pragma unroll
+        for (int q = 0; q < kI8Slices; q++) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
+        double mug = 0.0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int jl = g * 16 + e, j = jb * kAcqBM + jl;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < BOGP_MAX_DIM; k++)
+                if (k < dim) { const double df = pc[k] - xs[k][jl]; s += (df * df) * sl[k]; }
+            double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
+            if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
+            mug += al[jl] * v;
+            int d[kI8Slices];
+            balanced_digits(__double2ll_rn(ldexp(v, 54)), d);          // t = v / 2, fx = t * 2^55
+#pragma unroll
+            for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
+        }
+        mu += mug;
+        // k tile (32 rows) = jb*8 + g/2, k chunk = g & 1
+        uint8_t* dst = p.panel + ((int64_t)ct * (p.n_pad / kI8KB) + (int64_t)jb * (kAcqBM / kI8KB) + (g >> 1)) * kI8BTile
+                     + (g & 1) * (kI8Slices * kI8BN * 16) + nl * 16;
+#pragma unroll
+        for (int q = 0; q < kI8Slices; q++)
+            *reinterpret_cast<uint4*>(dst + q * (kI8BN * 16)) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+    }
+    mured[tid >> 6][nl] = mu;
+    __syncthreads();
+    if (tid < kI8BN) {                              // fixed-order sum of the 4 thread groups
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) s += mured[g][tid];
+        p.mupart[(int64_t)jb * p.S + (int64_t)ct * kI8BN + tid] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;      // next 16-byte k chunk
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;      // next group of 8 rows
+    d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+    return d;                                              // no swizzle, base offset 0
+}
+__host__ __device__ constexpr uint32_t umma_idesc_s8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D=s32, A=B=s8, K-major
+}
+__device__ __forceinline__ void umma_s8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "r"(taddr), "r"(z) : "memory");
+}
+
+struct TriI8Args {
+    const uint8_t* wq; const uint8_t* panel; const double* wscale; double* qpart;
+    int nI, nct, n_pad; int64_t S;
+};
+
+__global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full   = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kI8Stages * kI8Stage);
+    uint64_t* empt   = full + kI8Stages;
+    uint64_t* accbar = empt + kI8Stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accbar + 1);
+    double*   red    = reinterpret_cast<double*>(smem_raw + (size_t)kI8Stages * kI8Stage + 256);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ib = g.nI - 1 - (int)(blockIdx.x / g.nct);          // heaviest row blocks first
+    const int ct = (int)(blockIdx.x % g.nct);
+    const int nk = (ib + 1) * (kI8BM / kI8KB);
+
+    if (tid == 0) {
+        for (int s = 0; s < kI8Stages; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 1); }
+        mbar_init(accbar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {                                              // TMEM: all 512 columns (8 levels x 64 candidates)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= 2) {                                              // zero the accumulators (every MMA accumulates)
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int c = 0; c < 512; c += 8) tmem_st8_zero(tmem + lane_base + c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t* wsrc = g.wq + (int64_t)ib * (ib + 1) / 2 * (kI8BM / kI8KB) * kI8ATile;
+            const uint8_t* psrc = g.panel + (int64_t)ct * (g.n_pad / kI8KB) * kI8BTile;
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % kI8Stages;
+                if (kt >= kI8Stages) mbar_wait(&empt[s], ((kt / kI8Stages) - 1) & 1);
+                unsigned char* dst = smem_raw + (size_t)s * kI8Stage;
+                mbar_expect_tx(&full[s], kI8Stage);
+                bulk_g2s(dst, wsrc + (int64_t)kt * kI8ATile, kI8ATile, &full[s]);
+                bulk_g2s(dst + kI8ATile, psrc + (int64_t)kt * kI8BTile, kI8BTile, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % kI8Stages;
+                mbar_wait(&full[s], (kt / kI8Stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_u32(smem_raw + (size_t)s * kI8Stage);
+                const uint32_t b0 = a0 + kI8ATile;
+#pragma unroll
+                for (int p = 0; p < kI8Slices; p++) {
+                    const int nq = (8 - p) < kI8Slices ? (8 - p) : kI8Slices;     // panel slices q = 0..nq-1 -> levels p..p+nq-1
+                    const int ntot = nq * kI8BN;
+                    const uint64_t da = umma_desc_kmajor(a0 + p * (kI8BM * kI8KB), kI8BM * 16, 128);
+#pragma unroll
+                    for (int n0 = 0; n0 < ntot; n0 += 256) {
+                        const int nn = (ntot - n0) < 256 ? (ntot - n0) : 256;
+                        const uint64_t db = umma_desc_kmajor(b0 + n0 * 16, kI8Slices * kI8BN * 16, 128);
+                        umma_s8(tmem + (uint32_t)(p * kI8BN + n0), da, db, umma_idesc_s8(kI8BM, nn));
+                    }
+                }
+                umma_commit(&empt[s]);                            // stage reusable once these MMAs have read it
+            }
+            umma_commit(accbar);                                  // all MMAs done -> epilogue
+        }
+    } else {
+        mbar_wait(accbar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may read
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        const double scale = g.wscale[ib * kI8BM + q4 * 32 + lane];
+        for (int c0 = 0; c0 < kI8BN; c0 += 8) {
+            double acc[8];
+            {
+                uint32_t r[8];
+                tmem_ld8(tmem + lane_base + 7 * kI8BN + c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = (double)(int)r[j];
+            }
+#pragma unroll
+            for (int t = 6; t >= 0; t--) {                        // Horner in 2^-8
+                uint32_t r[8];
+                tmem_ld8(tmem + lane_base + t * kI8BN + c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fma(acc[j], 0.00390625, (double)(int)r[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double v = acc[j] * scale;
+                double s = v * v;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) red[q4 * kI8BN + c0 + j] = s;
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = tid - 64;
+        if (e < kI8BN) {
+            const double q = ((red[e] + red[kI8BN + e]) + red[2 * kI8BN + e]) + red[3 * kI8BN + e];
+            g.qpart[(int64_t)ib * g.S + (int64_t)ct * kI8BN + e] = q;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t i8_wq_bytes(int64_t n_pad) {
+    const int64_t nI = n_pad / kI8BM;
+    return (size_t)(nI * (nI + 1) / 2) * (kI8BM / kI8KB) * kI8ATile;
+}
+
+int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp, double* d_wscale, uint8_t* d_wq) {
+    row_exp_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, ctx->stream>>>(d_w, n_pad, (int)n_pad, d_wexp, d_wscale);
+    BOGP_LAUNCH_CHECK(ctx);
+    const int nI = (int)(n_pad / kI8BM);
+    slice_w_kernel<<<dim3(nI * (kI8BM / kI8KB), nI), 256, 0, ctx->stream>>>(d_w, n_pad, d_wexp, d_wq);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+size_t i8_panel_bytes(int64_t n_pad, int64_t S) { return (size_t)n_pad * S * kI8Slices; }
+
+int launch_acquire_chunk_i8(bogp_ctx* ctx, const AcqChunk& a) {
+    static bool configured = false;
+    if (!configured) {
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kI8Smem));
+        configured = true;
+    }
+    const int nct = (int)((a.cur + kI8BN - 1) / kI8BN);
+    PanelI8Args pa{};
+    pa.cand.points = a.points; pa.cand.axes = a.axes; pa.cand.cross_jitter = a.cross_jitter;
+    for (int k = 0; k < BOGP_MAX_DIM; k++) { pa.cand.len[k] = a.len[k]; pa.cand.off[k] = a.off[k]; }
+    pa.x_pad = a.x_pad; pa.inv_ell2 = a.inv_ell2; pa.alpha = a.alpha; pa.panel = (uint8_t*)a.panel; pa.mupart = a.mupart;
+    pa.c0 = a.c0; pa.c_end = a.c_end; pa.S = a.S; pa.n = a.n; pa.n_pad = a.n_pad; pa.dim = a.dim;
+    BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<<<dim3(nct, a.n_pad / kAcqBM), 256, 0, ctx->stream>>>(pa)));
+    BOGP_LAUNCH_CHECK(ctx);
+    const int nI = a.n_pad / kI8BM;
+    TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S};
+    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<nI * nct, 192, kI8Smem, ctx->stream>>>(ta)));
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+}  // namespace bogp

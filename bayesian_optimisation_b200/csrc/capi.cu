@@ -1,6 +1,7 @@
 // Context management and error reporting of libbogp.
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace bogp {
 static thread_local char g_error[512] = "";
@@ -35,6 +36,11 @@ extern "C" int bogp_create(int device, bogp_ctx** out) {
     bogp_ctx* c = new bogp_ctx();
     memset(c, 0, sizeof(*c));
     c->device = device; c->sm_count = prop.multiProcessorCount; c->stream = nullptr; c->launches = 0;
+    {
+        const char* e = getenv("BOGP_ACQUIRE_PATH");
+        c->acquire_path = (e && (!strcmp(e, "fp64") || !strcmp(e, "dmma") || !strcmp(e, "0"))) ? BOGP_PATH_FP64_DMMA
+                        : (e && (!strcmp(e, "i8") || !strcmp(e, "int8") || !strcmp(e, "1"))) ? BOGP_PATH_INT8_TCGEN05 : BOGP_PATH_DEFAULT;
+    }
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_block_score, kMaxReduceBlocks * sizeof(double)));
@@ -46,6 +52,13 @@ extern "C" int bogp_create(int device, bogp_ctx** out) {
     *out = c;
     return BOGP_OK;
 }
+
+extern "C" int bogp_set_acquire_path(bogp_ctx* ctx, int path) {
+    if (!ctx || (path != BOGP_PATH_FP64_DMMA && path != BOGP_PATH_INT8_TCGEN05)) { set_error("bogp_set_acquire_path: bad argument"); return BOGP_ERR_BAD_ARG; }
+    ctx->acquire_path = path;
+    return BOGP_OK;
+}
+extern "C" int bogp_get_acquire_path(const bogp_ctx* ctx) { return ctx ? ctx->acquire_path : -1; }
 
 extern "C" int bogp_profile(bogp_ctx* ctx, int enable) {
     if (!ctx) { set_error("bogp_profile: null context"); return BOGP_ERR_BAD_ARG; }

@@ -72,6 +72,7 @@ struct bogp_ctx {
     long long*   d_block_index; // kMaxBlocks
     double*      h_pinned;      // 64 doubles pinned host staging
     // optional per-kernel timing of the acquisition sweep (bogp_profile): CUDA events on the launching stream
+    int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
     cudaEvent_t  ev[2];
     double       prof_ms[8];

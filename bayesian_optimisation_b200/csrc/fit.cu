@@ -326,7 +326,8 @@ using namespace bogp;
 // ================================================================================================
 struct bogp_fit {
     int64_t n, n_pad; int dim;
-    double *x_pad, *y_pad, *inv_ell2, *a, *w, *wp, *t, *alpha, *v, *scalars;
+    double *x_pad, *y_pad, *inv_ell2, *a, *w, *wp, *t, *alpha, *v, *scalars, *wscale;
+    uint8_t* wq; int* wexp;
     int* info;
     double jitter;
     bogp_ctx* ctx;
@@ -334,7 +335,7 @@ struct bogp_fit {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct FitLayout { size_t x, y, ell, a, w, wp, alpha, v, scal, info, total; };
+struct FitLayout { size_t x, y, ell, a, w, wp, alpha, v, scal, info, wq, wexp, wscale, total; };
 static FitLayout fit_layout(int64_t n, int dim) {
     const int64_t np = (n + kPad - 1) / kPad * kPad;
     FitLayout l{}; size_t off = 0;
@@ -346,6 +347,7 @@ static FitLayout fit_layout(int64_t n, int dim) {
     // separate when the scratch is the larger one (ragged block counts)
     l.wp = take((shared > tneed ? shared : tneed) * 8);
     l.alpha = take(np * 8); l.v = take(np * 8); l.scal = take(64 * 8); l.info = take(64 * 4);
+    l.wq = take(i8_wq_bytes(np)); l.wexp = take(np * 4); l.wscale = take(np * 8);
     l.total = off;
     return l;
 }
@@ -386,6 +388,7 @@ extern "C" int bogp_fit_create(bogp_ctx* ctx, const double* d_x, const double* d
     const int64_t np = (n + kPad - 1) / kPad * kPad; f->n_pad = np;
     f->x_pad = (double*)(base + l.x); f->y_pad = (double*)(base + l.y); f->inv_ell2 = (double*)(base + l.ell);
     f->a = (double*)(base + l.a); f->w = (double*)(base + l.w); f->wp = (double*)(base + l.wp); f->t = f->wp;
+    f->wq = (uint8_t*)(base + l.wq); f->wexp = (int*)(base + l.wexp); f->wscale = (double*)(base + l.wscale);
     f->alpha = (double*)(base + l.alpha); f->v = (double*)(base + l.v); f->scalars = (double*)(base + l.scal); f->info = (int*)(base + l.info);
     cudaStream_t st = ctx->stream;
     int rc;
@@ -412,6 +415,8 @@ extern "C" int bogp_fit_create(bogp_ctx* ctx, const double* d_x, const double* d
         dim3 grid(nI * (kAcqBM / kAcqKB), nI);
         pack_w_kernel<<<grid, 256, 0, st>>>(f->w, np, f->wp); ctx->launches++;
     }
+    // digit tiles of W for the INT8 tensor path
+    FIT_TRY(launch_slice_w(ctx, f->w, np, f->wexp, f->wscale, f->wq));
     FIT_CUDA(cudaGetLastError());
     // status + nlml back to the host
     int info = 0; double sc[3];
@@ -445,6 +450,8 @@ extern "C" double bogp_fit_logdet(const bogp_fit* fit) {
 // accessors used by acquire.cu
 namespace bogp {
 const double* fit_wp(const bogp_fit* f) { return f->wp; }
+const uint8_t* fit_wq(const bogp_fit* f) { return f->wq; }
+const double* fit_wscale(const bogp_fit* f) { return f->wscale; }
 const double* fit_xpad(const bogp_fit* f) { return f->x_pad; }
 const double* fit_inv_ell2(const bogp_fit* f) { return f->inv_ell2; }
 const double* fit_alpha(const bogp_fit* f) { return f->alpha; }

@@ -20,6 +20,23 @@ int trtri_recursive(bogp_ctx* ctx, const double* d_l, int64_t ldl, int64_t strid
                     int64_t strideW, double* d_t, int64_t strideT, int64_t n, int batch);
 size_t packed_w_doubles(int64_t n_pad);
 
+// one chunk of the acquisition sweep, as handed to either tensor path
+struct AcqChunk {
+    const double* points; const double* axes; int len[BOGP_MAX_DIM]; int off[BOGP_MAX_DIM]; double cross_jitter;
+    const double* x_pad; const double* inv_ell2; const double* alpha;
+    const double* wp;                 // FP64 path: fragment-packed W
+    const uint8_t* wq; const double* wscale;   // INT8 path: digit tiles of W + row scales
+    void* panel; double* qpart; double* mupart;
+    int64_t c0, c_end, cur, S;
+    int n, n_pad, dim;
+};
+int launch_acquire_chunk_i8(bogp_ctx* ctx, const AcqChunk& a);
+size_t i8_wq_bytes(int64_t n_pad);
+size_t i8_panel_bytes(int64_t n_pad, int64_t S);
+int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp, double* d_wscale, uint8_t* d_wq);
+const uint8_t* fit_wq(const bogp_fit* f);
+const double* fit_wscale(const bogp_fit* f);
+
 const double* fit_wp(const bogp_fit* f);
 const double* fit_xpad(const bogp_fit* f);
 const double* fit_inv_ell2(const bogp_fit* f);

@@ -127,6 +127,15 @@ class GPEngine:
     def sm_count(self) -> int:
         return int(self.lib.bogp_sm_count(self._ctx))
 
+    @property
+    def acquire_path(self) -> str:
+        return "i8" if self.lib.bogp_get_acquire_path(self._ctx) == _lib.PATH_INT8_TCGEN05 else "fp64"
+
+    def set_acquire_path(self, path: str):
+        """"fp64": DMMA on the FP64 pipe; "i8": exact digit slices on tcgen05 kind::i8 (include/bogp.h)."""
+        code = {"fp64": _lib.PATH_FP64_DMMA, "dmma": _lib.PATH_FP64_DMMA, "i8": _lib.PATH_INT8_TCGEN05, "int8": _lib.PATH_INT8_TCGEN05}[path]
+        _lib.check(self.lib.bogp_set_acquire_path(self._ctx, code))
+
     def profile(self, enable: bool):
         """Per-kernel CUDA-event timing of the acquisition sweep (measurement aid; serialises the stream)."""
         _lib.check(self.lib.bogp_profile(self._ctx, 1 if enable else 0))
@@ -191,7 +200,7 @@ class GPEngine:
     # ------------------------------------------------------------------ K4
     def acquire(self, fit: GPFit, candidates, c_begin: int = 0, c_end: Optional[int] = None, kind: int = ACQ_LCB,
                 explore: float = 4.0, f_best: float = 0.0, prior_diag: float = PRIOR_DIAG, outputs: bool = False,
-                chunk: int = 8192, cross_jitter: float = 0.0) -> AcquireResult:
+                chunk: Optional[int] = None, cross_jitter: float = 0.0) -> AcquireResult:
         """Score flat candidate indices [c_begin, c_end) and return the best (score, index).
 
         `candidates`: CandidateGrid, or an explicit (C, d) array (numpy -> copied to HBM, or a
@@ -216,6 +225,8 @@ class GPEngine:
         total = int(cd.c_total)
         c_end = total if c_end is None else int(c_end)
         count = c_end - int(c_begin)
+        if chunk is None:      # candidates per kernel chunk: a k_* panel of about 512 MB
+            chunk = min(65536, max(8192, (512 << 20) // (fit.n_pad * 8)))
         chunk = max(64, min(int(chunk), (count + 63) // 64 * 64))
         need = self.lib.bogp_acquire_workspace_bytes(fit._h, chunk)
         if self._acq_ws is None or self._acq_ws.numel() < need:

@@ -162,7 +162,7 @@ def workload_config(cands, gpus):
                         f"contiguous {cands}-candidate slice per GPU of the {GRID_PTS}^{DIM}=1e8-point grid (BASELINE.json configs[2])",
             "n_obs": N_OBS, "dim": DIM, "candidates_per_step_per_gpu": cands, "grid_points_per_axis": GRID_PTS,
             "acquisition": "EI", "sharding": f"contiguous flat-index slices x{gpus}, Cholesky replicated, 16-byte all_gather max-loc",
-            "l2": "per-step working set (k_* panel 268 MB + W 67 MB, re-streamed per 8192-candidate chunk) exceeds the 126 MB L2; no flush needed"}
+            "l2": "per-step working set (k_* panel 537 MB + W 67 MB, re-streamed per kernel chunk) exceeds the 126 MB L2; no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -351,8 +351,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cands", type=int, default=1 << 20, help="candidates per step per GPU")
-    ap.add_argument("--chunk", type=int, default=8192, help="candidates per kernel chunk")
-    ap.add_argument("--e2e-cands", type=int, default=1 << 18)
+    ap.add_argument("--chunk", type=int, default=16384, help="candidates per kernel chunk")
+    ap.add_argument("--e2e-cands", type=int, default=1 << 20)
     ap.add_argument("--ref-sample", type=int, default=8192, help="candidates per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -51,6 +51,17 @@ int  bogp_set_stream(bogp_ctx* ctx, void* cuda_stream);
 int  bogp_sm_count(const bogp_ctx* ctx);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t bogp_launch_count(const bogp_ctx* ctx);
+/* Which tensor path the acquisition product V = L^-1 k_* runs on:
+ *   BOGP_PATH_FP64_DMMA    mma.sync DMMA.8x8x4 on the FP64 pipe (the straightforward fp64 product);
+ *   BOGP_PATH_INT8_TCGEN05 exact integer digit slices on tcgen05.mma kind::i8 with TMEM accumulators
+ *                          (error-free splitting; result agrees with the fp64 product to < 2^-50 of the
+ *                          row scale and is independent of any summation order).
+ * Default: environment variable BOGP_ACQUIRE_PATH ("fp64" | "i8"), else BOGP_PATH_DEFAULT.            */
+#define BOGP_PATH_FP64_DMMA     0
+#define BOGP_PATH_INT8_TCGEN05  1
+#define BOGP_PATH_DEFAULT       BOGP_PATH_FP64_DMMA
+int bogp_set_acquire_path(bogp_ctx* ctx, int path);
+int bogp_get_acquire_path(const bogp_ctx* ctx);
 /* Measurement aid: when enabled, each kernel of the acquisition sweep is bracketed by CUDA
  * events on the launching stream (this serialises the stream; never enable it inside a timed
  * region).  kernel_id: 0 panel, 1 tri-GEMM, 2 finalize, 3 merge.                            */
