@@ -39,9 +39,10 @@ struct PanelArgs {
 // grid (ceil(cur/64), n_pad/256), 256 threads: warp w <-> candidates 8w..8w+7 of the tile,
 // lane = (cand % 8) * 4 + (j % 4): exactly the B-fragment order of DMMA.8x8x4, so each warp
 // store is one contiguous 256-byte line of the packed panel.
+template <int DIMP>
 __global__ void __launch_bounds__(256) panel_kernel(PanelArgs p) {
     __shared__ __align__(128) double ps_raw[kAcqBN * BOGP_MAX_DIM];   // candidate block, [cand][dim] as in HBM
-    __shared__ double xs[BOGP_MAX_DIM][kAcqBM + 1];
+    __shared__ double xs[DIMP][kAcqBM + 1];
     __shared__ double al[kAcqBM];
     __shared__ double sl[BOGP_MAX_DIM];
     __shared__ __align__(8) uint64_t bar;
@@ -68,12 +69,12 @@ __global__ void __launch_bounds__(256) panel_kernel(PanelArgs p) {
         }
     }
     // measured points of this row block, transposed; alpha; 1/ell^2
-    for (int i = tid; i < kAcqBM * dim; i += 256) {
-        int r = i / dim, k = i % dim;
-        xs[k][r] = p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k];
+    for (int i = tid; i < kAcqBM * DIMP; i += 256) {
+        int r = i / DIMP, k = i % DIMP;
+        xs[k][r] = k < dim ? p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k] : 0.0;
     }
     al[tid] = p.alpha[jb * kAcqBM + tid];
-    if (tid < dim) sl[tid] = p.inv_ell2[tid];
+    if (tid < BOGP_MAX_DIM) sl[tid] = tid < dim ? p.inv_ell2[tid] : 0.0;
 
     if (explicit_mode) {
         if (used_tma) {
@@ -95,9 +96,9 @@ __global__ void __launch_bounds__(256) panel_kernel(PanelArgs p) {
     const int nl = warp * 8 + (lane >> 2), jj = lane & 3;
     const int64_t cglob = cbase + nl;
     const int ncl = nl < nvalid ? nl : nvalid - 1;     // tail tiles recompute the last valid candidate; masked later
-    double pc[BOGP_MAX_DIM];
+    double pc[DIMP], il[DIMP];      // padded dimensions carry zeros and add exactly +0
 #pragma unroll
-    for (int k = 0; k < BOGP_MAX_DIM; k++) pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0;
+    for (int k = 0; k < DIMP; k++) { pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0; il[k] = sl[k]; }
 
     double* tile0 = p.panel + ((int64_t)ct * (p.n_pad / kAcqKB) + (int64_t)jb * (kAcqBM / kAcqKB)) * (kAcqKB * kAcqBN);
     double mu = 0.0;
@@ -106,9 +107,7 @@ __global__ void __launch_bounds__(256) panel_kernel(PanelArgs p) {
         const int j = jb * kAcqBM + jl;
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < BOGP_MAX_DIM; k++) {
-            if (k < dim) { const double df = pc[k] - xs[k][jl]; s += (df * df) * sl[k]; }
-        }
+        for (int k = 0; k < DIMP; k++) { const double df = pc[k] - xs[k][jl]; s += (df * df) * il[k]; }
         double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
         if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
         mu += al[jl] * v;
@@ -396,7 +395,12 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
             nIq = (int)(n_pad / 128);
         } else {
             PanelArgs pa{cd, fit_xpad(fit), fit_inv_ell2(fit), fit_alpha(fit), panel, mupart, c0, c_end, S, (int)fit_n(fit), (int)n_pad, dim};
-            BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_kernel<<<dim3(nct, nI), 256, 0, st>>>(pa))); BOGP_LAUNCH_CHECK(ctx);
+#define BOGP_PANEL(D) BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_kernel<D><<<dim3(nct, nI), 256, 0, st>>>(pa)))
+            if (dim <= 2) BOGP_PANEL(2); else if (dim <= 4) BOGP_PANEL(4); else if (dim <= 6) BOGP_PANEL(6);
+            else if (dim <= 8) BOGP_PANEL(8); else if (dim <= 10) BOGP_PANEL(10); else if (dim <= 12) BOGP_PANEL(12);
+            else BOGP_PANEL(16);
+#undef BOGP_PANEL
+            BOGP_LAUNCH_CHECK(ctx);
             TriArgs ta{fit_wp(fit), panel, qpart, nI, nct, (int)n_pad, S};
             BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta))); BOGP_LAUNCH_CHECK(ctx);
             nIq = nI;

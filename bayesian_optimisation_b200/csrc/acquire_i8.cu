@@ -110,9 +110,28 @@ struct PanelI8Args {
     int n, n_pad, dim;
 };
 
-__global__ void __launch_bounds__(256) panel_i8_kernel(PanelI8Args p) {
+// 4x4 byte transpose: out[m] = (byte m of w0, byte m of w1, byte m of w2, byte m of w3)
+__device__ __forceinline__ void transpose4x4_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t (&out)[4]) {
+    const uint32_t a = __byte_perm(w0, w1, 0x5140);   // w0.b0 w1.b0 w0.b1 w1.b1
+    const uint32_t b = __byte_perm(w2, w3, 0x5140);
+    const uint32_t c = __byte_perm(w0, w1, 0x7362);   // w0.b2 w1.b2 w0.b3 w1.b3
+    const uint32_t d = __byte_perm(w2, w3, 0x7362);
+    out[0] = __byte_perm(a, b, 0x5410);
+    out[1] = __byte_perm(a, b, 0x7632);
+    out[2] = __byte_perm(c, d, 0x5410);
+    out[3] = __byte_perm(c, d, 0x7632);
+}
+
+// UB = true : k >= 0, so the 7 low bytes of the fixed-point value ARE its base-256 digits (unsigned
+//             operand for the MMA; no digit arithmetic at all, just byte transposes).  Allowed while
+//             7 * n_pad * 128 * 255 < 2^31, i.e. n_pad <= 8192.
+// UB = false: balanced signed digits (|digit| <= 128), safe up to n_pad = 16384.
+// DIMP = feature count rounded up to an instantiated size; the extra dimensions carry zeros
+// (coordinate 0, 1/ell^2 = 0) and add exactly +0 to the squared distance.
+template <int DIMP, bool UB>
+__global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     __shared__ __align__(128) double ps_raw[kI8BN * BOGP_MAX_DIM];
-    __shared__ double xs[BOGP_MAX_DIM][kAcqBM + 1];
+    __shared__ double xs[DIMP][kAcqBM + 1];
     __shared__ double al[kAcqBM];
     __shared__ double sl[BOGP_MAX_DIM];
     __shared__ double mured[4][kI8BN];
@@ -135,12 +154,12 @@ __global__ void __launch_bounds__(256) panel_i8_kernel(PanelI8Args p) {
             if (tid == 0) { mbar_expect_tx(&bar, bytes); bulk_g2s(ps_raw, src, bytes, &bar); }
         }
     }
-    for (int i = tid; i < kAcqBM * dim; i += 256) {
-        int r = i / dim, k = i % dim;
-        xs[k][r] = p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k];
+    for (int i = tid; i < kAcqBM * DIMP; i += 256) {
+        int r = i / DIMP, k = i % DIMP;
+        xs[k][r] = k < dim ? p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k] : 0.0;
     }
     al[tid] = p.alpha[jb * kAcqBM + tid];
-    if (tid < dim) sl[tid] = p.inv_ell2[tid];
+    if (tid < BOGP_MAX_DIM) sl[tid] = tid < dim ? p.inv_ell2[tid] : 0.0;
     if (explicit_mode) {
         if (used_tma) mbar_wait(&bar, 0);
         else for (int i = tid; i < nvalid * dim; i += 256) ps_raw[i] = p.cand.points[cbase * dim + i];
@@ -156,31 +175,54 @@ __global__ void __launch_bounds__(256) panel_i8_kernel(PanelI8Args p) {
 
     const int nl = tid & 63;                       // candidate within the tile
     const int ncl = nl < nvalid ? nl : nvalid - 1;
-    double pc[BOGP_MAX_DIM];
+    double pc[DIMP], il[DIMP];
 #pragma unroll
-    for (int k = 0; k < BOGP_MAX_DIM; k++) pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0;
+    for (int k = 0; k < DIMP; k++) { pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0; il[k] = sl[k]; }
     const int64_t cglob = cbase + nl;
     double mu = 0.0;      // this thread's 4 row groups, ascending
     // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
     for (int g = tid >> 6; g < kAcqBM / 16; g += 4) {
         uint32_t pk[kI8Slices][4];
-#pragma unroll
-        for (int q = 0; q < kI8Slices; q++) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
         double mug = 0.0;
+        if (UB) {
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            const int jl = g * 16 + e, j = jb * kAcqBM + jl;
-            double s = 0.0;
+            for (int e4 = 0; e4 < 4; e4++) {
+                uint32_t lo[4], hi[4];
 #pragma unroll
-            for (int k = 0; k < BOGP_MAX_DIM; k++)
-                if (k < dim) { const double df = pc[k] - xs[k][jl]; s += (df * df) * sl[k]; }
-            double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
-            if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
-            mug += al[jl] * v;
-            int d[kI8Slices];
-            balanced_digits(__double2ll_rn(ldexp(v, 54)), d);          // t = v / 2, fx = t * 2^55
+                for (int i = 0; i < 4; i++) {
+                    const int jl = g * 16 + e4 * 4 + i, j = jb * kAcqBM + jl;
+                    double s = 0.0;
 #pragma unroll
-            for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
+                    for (int k = 0; k < DIMP; k++) { const double df = pc[k] - xs[k][jl]; s += (df * df) * il[k]; }
+                    double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
+                    if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
+                    mug += al[jl] * v;
+                    const unsigned long long fx = __double2ull_rn(v * 18014398509481984.0);   // t = v / 2, fx = t * 2^55 = v * 2^54 (exact scaling)
+                    lo[i] = (uint32_t)fx; hi[i] = (uint32_t)(fx >> 32);
+                }
+                uint32_t tl[4], th[4];
+                transpose4x4_bytes(lo[0], lo[1], lo[2], lo[3], tl);      // digits 0..3 (least significant first)
+                transpose4x4_bytes(hi[0], hi[1], hi[2], hi[3], th);      // digits 4..6
+                pk[6][e4] = tl[0]; pk[5][e4] = tl[1]; pk[4][e4] = tl[2]; pk[3][e4] = tl[3];
+                pk[2][e4] = th[0]; pk[1][e4] = th[1]; pk[0][e4] = th[2];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kI8Slices; q++) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int jl = g * 16 + e, j = jb * kAcqBM + jl;
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIMP; k++) { const double df = pc[k] - xs[k][jl]; s += (df * df) * il[k]; }
+                double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
+                if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
+                mug += al[jl] * v;
+                int d[kI8Slices];
+                balanced_digits(__double2ll_rn(v * 18014398509481984.0), d);   // t = v / 2, fx = t * 2^55 = v * 2^54
+#pragma unroll
+                for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
+            }
         }
         mu += mug;
         // k tile (32 rows) = jb*8 + g/2, k chunk = g & 1
@@ -211,13 +253,14 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lb
     d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
     return d;                                              // no swizzle, base offset 0
 }
-__host__ __device__ constexpr uint32_t umma_idesc_s8(int M, int N) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D=s32, A=B=s8, K-major
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N, int b_signed) {
+    // D = s32, A = s8, B = s8 / u8, both K-major
+    return (2u << 4) | (1u << 7) | ((uint32_t)(b_signed ? 1 : 0) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_s8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
-                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -233,7 +276,7 @@ __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
 
 struct TriI8Args {
     const uint8_t* wq; const uint8_t* panel; const double* wscale; double* qpart;
-    int nI, nct, n_pad; int64_t S;
+    int nI, nct, n_pad; int64_t S; int b_signed; int group;   // group = candidate tiles scheduled together (L2 reuse of the panel)
 };
 
 __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
@@ -245,8 +288,14 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
     double*   red    = reinterpret_cast<double*>(smem_raw + (size_t)kI8Stages * kI8Stage + 256);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ib = g.nI - 1 - (int)(blockIdx.x / g.nct);          // heaviest row blocks first
-    const int ct = (int)(blockIdx.x % g.nct);
+    // CTA order: groups of `group` candidate tiles; inside a group the heaviest row blocks first.  CTAs
+    // that run together then share the group's panel tiles (and the W row block) in L2.
+    const int per_group = g.nI * g.group;
+    const int grp = (int)(blockIdx.x / per_group), rem = (int)(blockIdx.x % per_group);
+    const int gc = min(g.group, g.nct - grp * g.group);
+    const int ib = g.nI - 1 - rem / gc;
+    const int ct = grp * g.group + rem % gc;
+    if (ib < 0) return;                                           // padding CTAs of the last (partial) group
     const int nk = (ib + 1) * (kI8BM / kI8KB);
 
     if (tid == 0) {
@@ -263,9 +312,10 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 2) {                                              // zero the accumulators (every MMA accumulates)
+    if (warp >= 2) {   // level 7 is first touched by an accumulating MMA: zero it.  Levels 0..6 are initialised
+                       // by the first (non-accumulating) MMAs of slice 0.
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        for (int c = 0; c < 512; c += 8) tmem_st8_zero(tmem + lane_base + c);
+        for (int c = 7 * kI8BN; c < 8 * kI8BN; c += 8) tmem_st8_zero(tmem + lane_base + c);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -302,7 +352,7 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
                     for (int n0 = 0; n0 < ntot; n0 += 256) {
                         const int nn = (ntot - n0) < 256 ? (ntot - n0) : 256;
                         const uint64_t db = umma_desc_kmajor(b0 + n0 * 16, kI8Slices * kI8BN * 16, 128);
-                        umma_s8(tmem + (uint32_t)(p * kI8BN + n0), da, db, umma_idesc_s8(kI8BM, nn));
+                        umma_i8(tmem + (uint32_t)(p * kI8BN + n0), da, db, umma_idesc_i8(kI8BM, nn, g.b_signed), (p > 0 || kt > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empt[s]);                            // stage reusable once these MMAs have read it
@@ -316,21 +366,17 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         const double scale = g.wscale[ib * kI8BM + q4 * 32 + lane];
         for (int c0 = 0; c0 < kI8BN; c0 += 8) {
+            uint32_t r[8][8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) tmem_ld8(tmem + lane_base + t * kI8BN + c0, r[t]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             double acc[8];
-            {
-                uint32_t r[8];
-                tmem_ld8(tmem + lane_base + 7 * kI8BN + c0, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[j] = (double)(int)r[j];
-            }
+            for (int j = 0; j < 8; j++) {
+                double a = (double)(int)r[7][j];
 #pragma unroll
-            for (int t = 6; t >= 0; t--) {                        // Horner in 2^-8
-                uint32_t r[8];
-                tmem_ld8(tmem + lane_base + t * kI8BN + c0, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 8; j++) acc[j] = fma(acc[j], 0.00390625, (double)(int)r[j]);
+                for (int t = 6; t >= 0; t--) a = fma(a, 0.00390625, (double)(int)r[t][j]);      // Horner in 2^-8 (exact products)
+                acc[j] = a;
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -382,11 +428,24 @@ int launch_acquire_chunk_i8(bogp_ctx* ctx, const AcqChunk& a) {
     for (int k = 0; k < BOGP_MAX_DIM; k++) { pa.cand.len[k] = a.len[k]; pa.cand.off[k] = a.off[k]; }
     pa.x_pad = a.x_pad; pa.inv_ell2 = a.inv_ell2; pa.alpha = a.alpha; pa.panel = (uint8_t*)a.panel; pa.mupart = a.mupart;
     pa.c0 = a.c0; pa.c_end = a.c_end; pa.S = a.S; pa.n = a.n; pa.n_pad = a.n_pad; pa.dim = a.dim;
-    BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<<<dim3(nct, a.n_pad / kAcqBM), 256, 0, ctx->stream>>>(pa)));
+    const bool ub = a.n_pad <= 8192;      // unsigned panel digits while the int32 level sums cannot overflow
+    const dim3 pgrid(nct, a.n_pad / kAcqBM);
+#define BOGP_PANEL_I8(D)                                                                                              \
+    do {                                                                                                              \
+        if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true><<<pgrid, 256, 0, ctx->stream>>>(pa))); }  \
+        else    { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false><<<pgrid, 256, 0, ctx->stream>>>(pa))); } \
+    } while (0)
+    if (a.dim <= 2) BOGP_PANEL_I8(2); else if (a.dim <= 4) BOGP_PANEL_I8(4); else if (a.dim <= 6) BOGP_PANEL_I8(6);
+    else if (a.dim <= 8) BOGP_PANEL_I8(8); else if (a.dim <= 10) BOGP_PANEL_I8(10); else if (a.dim <= 12) BOGP_PANEL_I8(12);
+    else BOGP_PANEL_I8(16);
+#undef BOGP_PANEL_I8
     BOGP_LAUNCH_CHECK(ctx);
     const int nI = a.n_pad / kI8BM;
-    TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S};
-    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<nI * nct, 192, kI8Smem, ctx->stream>>>(ta)));
+    int group = (int)((32u << 20) / ((size_t)(a.n_pad / kI8KB) * kI8BTile));     // ~32 MB of panel per group
+    group = group < 1 ? 1 : (group > 64 ? 64 : group);
+    const int ngroups = (nct + group - 1) / group;
+    TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S, ub ? 0 : 1, group};
+    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<ngroups * nI * group, 192, kI8Smem, ctx->stream>>>(ta)));
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }

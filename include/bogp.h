@@ -59,7 +59,7 @@ int64_t bogp_launch_count(const bogp_ctx* ctx);
  * Default: environment variable BOGP_ACQUIRE_PATH ("fp64" | "i8"), else BOGP_PATH_DEFAULT.            */
 #define BOGP_PATH_FP64_DMMA     0
 #define BOGP_PATH_INT8_TCGEN05  1
-#define BOGP_PATH_DEFAULT       BOGP_PATH_FP64_DMMA
+#define BOGP_PATH_DEFAULT       BOGP_PATH_INT8_TCGEN05
 int bogp_set_acquire_path(bogp_ctx* ctx, int path);
 int bogp_get_acquire_path(const bogp_ctx* ctx);
 /* Measurement aid: when enabled, each kernel of the acquisition sweep is bracketed by CUDA

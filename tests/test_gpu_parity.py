@@ -12,10 +12,26 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(scope="module")
-def eng():
-    from bayesian_optimisation_b200.engine import GPEngine
-    return GPEngine(0)
+_ENGINE = None
+
+
+@pytest.fixture(params=["i8", "fp64"], autouse=True)
+def acquire_path(request):
+    """Every test runs on both tensor paths of the acquisition product (include/bogp.h):
+    "i8" = exact digit slices on tcgen05 kind::i8 (default), "fp64" = DMMA on the FP64 pipe."""
+    from bayesian_optimisation_b200 import engine as e
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = e.GPEngine(0)
+    _ENGINE.set_acquire_path(request.param)
+    e.default_engine().set_acquire_path(request.param)
+    yield request.param
+    e.default_engine().set_acquire_path("i8")
+
+
+@pytest.fixture
+def eng(acquire_path):
+    return _ENGINE
 
 
 def _consts():
@@ -161,6 +177,24 @@ def test_expected_improvement_matches_oracle(eng):
     mu_ref, var_ref = o.posterior_diag(X, y, o.candidate_grid(axes), ell, return_var=True)
     ei_full = o.expected_improvement(mu_ref, np.sqrt(np.abs(var_ref)), fb)
     assert res.best_index == int(np.flatnonzero(ei_full == ei_full.max())[0])
+
+
+def test_the_two_tensor_paths_agree(eng):
+    """INT8 digit-slice product vs FP64 DMMA product of the same fit: sigma^2 within 1e-12 absolute
+    (both are within rounding of the exact product), identical winner."""
+    from bayesian_optimisation_b200.engine import CandidateGrid
+    e = _consts()
+    X, y, ell = o.synthetic_problem(1500, 7, seed=9)
+    grid = CandidateGrid([np.linspace(0, 1, 4)] * 7)
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    out = {}
+    for path in ("fp64", "i8"):
+        eng.set_acquire_path(path)
+        assert eng.acquire_path == path
+        out[path] = eng.acquire(fit, grid, outputs=True)
+    np.testing.assert_allclose(out["i8"].sigma.cpu().numpy() ** 2, out["fp64"].sigma.cpu().numpy() ** 2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["i8"].mu.cpu().numpy(), out["fp64"].mu.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    assert out["i8"].best_index == out["fp64"].best_index
 
 
 def test_sharded_ranges_are_bit_identical_and_pick_the_same_index(eng):
