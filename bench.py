@@ -202,6 +202,8 @@ def run_gpu_arm(args):
         os.environ["NCCL_DEBUG"] = os.environ.get("BOGP_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     eng = GPEngine(local)
+    if args.path:
+        eng.set_acquire_path(args.path)
     X, y, ell = synthetic()
     f_best = float(y.min())
     grid = CandidateGrid([np.linspace(0.0, 1.0, GRID_PTS)] * DIM)
@@ -266,6 +268,7 @@ def run_gpu_arm(args):
     def e2e_step(k):
         b, _ = step_range(k)
         ps = PointSelector()
+        ps._engine = eng                        # same context / tensor path as the device-resident leg
         ps.name, ps.iteration = "bench", k
         ps.measured_pts, ps.measured_vals = X, y
         ps.feature_domain = [e2e_cands]
@@ -292,37 +295,61 @@ def run_gpu_arm(args):
     h2d = (N_OBS * DIM + N_OBS) * 8 * 2 + e2e_cands * DIM * 8 + 2 * DIM * 8
     d2h = 3 * e2e_cands * 8 + 8 + 16 + 16
 
-    # ---- roofline of the dominant kernel (tri-GEMM), per-launch CUDA-event timing in a separate pass
+    # ---- roofline of the dominant kernel (the acquisition product V = L^-1 k_*), per-launch CUDA-event
+    #      timing in a separate pass (the hooks serialise the stream, so never inside the timed steps)
     roof, cpu_base, fp64_peak = None, None, None
     if rank == 0:
         fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
         eng.profile(True)
-        eng.acquire(fit, grid, 0, min(cands, 32 * args.chunk), kind=ACQ_EI, f_best=f_best, chunk=args.chunk)
-        prof = eng.profile_read()
+        eng.acquire(fit, grid, 0, min(cands, 16 * args.chunk), kind=ACQ_EI, f_best=f_best, chunk=args.chunk)
+        prof = {k: v for k, v in eng.profile_read().items() if k in ("panel", "trigemm", "finalize", "merge")}
         eng.profile(False)
+        n_pad = fit.n_pad
         fit.close()
         fp64_peak = measure_fp64_peak(torch, dev)
         tri_ms, tri_n = prof["trigemm"]
         per_launch_ms = tri_ms / max(1, tri_n)
         chunk_c = min(args.chunk, cands)
-        flops = float(N_OBS) ** 2 * chunk_c                      # N^2 flops per candidate (triangular product)
-        achieved = flops / (per_launch_ms * 1e-3) * 1e-12
-        dmma_peak = 37.0                                          # DMMA issue-rate peak measured with tools/dmma_bench (profiles/)
-        peak = max(fp64_peak, dmma_peak)
+        flops = float(N_OBS) ** 2 * chunk_c                      # N^2 fp64 flops per candidate (triangular product)
+        fp64_equiv = flops / (per_launch_ms * 1e-3) * 1e-12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
         traffic = None
         tj = os.path.join(ROOT, "profiles", "trigemm_traffic.json")
         if os.path.isfile(tj):
             try:
-                traffic = json.load(open(tj)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tj)).get(eng.acquire_path, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         total_prof = sum(v[0] for v in prof.values())
-        roof = {"bound": "tensor", "kernel": "trigemm_kernel (FP64 DMMA)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "ms_per_launch": per_launch_ms, "launches_timed": tri_n,
-                "algorithmic_flops_per_launch": flops,
-                "peak_source": f"fp64 is not in MEASURED_PEAKS.json: max(cuBLAS DGEMM 6144^3 measured live = {fp64_peak:.1f} TF/s, "
-                               f"DMMA.8x8x4 issue-rate microbenchmark tools/dmma_bench = {dmma_peak} TF/s)",
-                "share_of_sweep": {k: v[0] / total_prof for k, v in prof.items()} if total_prof > 0 else None}
+        share = {k: v[0] / total_prof for k, v in prof.items()} if total_prof > 0 else None
+        if eng.acquire_path == "i8":
+            # executed integer work: 34 digit pairs x n_pad*(n_pad+128)/2 MACs per candidate, 2 ops per MAC
+            int8_ops = 34.0 * n_pad * (n_pad + 128) * chunk_c
+            achieved = int8_ops / (per_launch_ms * 1e-3) * 1e-12
+            bf16 = peaks.get("bf16_tflops")
+            peak = 2.0 * bf16 if bf16 else 2.0 * 1590.0
+            roof = {"bound": "tensor", "kernel": "trigemm_i8_kernel (tcgen05.mma kind::i8, TMEM accumulators; exact digit-slice fp64 product)",
+                    "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "ms_per_launch": per_launch_ms, "launches_timed": tri_n, "executed_int8_ops_per_launch": int8_ops,
+                    "algorithmic_flops_per_launch": flops, "fp64_equivalent_tflops": fp64_equiv,
+                    "fp64_pipe_peak_tflops": max(fp64_peak, 37.0), "frac_of_fp64_pipe_peak": fp64_equiv / max(fp64_peak, 37.0),
+                    "peak_source": ("dense int8 tensor peak taken as 2 x the measured cuBLAS bf16 burst figure of MEASURED_PEAKS.json "
+                                    f"({bf16} TF/s; int8 runs at twice the bf16 rate, nominal 4500 vs 2250) -- of measured"
+                                    if bf16 else "2 x the fallback bf16 figure 1590 TF/s -- of fallback"),
+                    "share_of_sweep": share}
+        else:
+            dmma_peak = 37.0                                      # DMMA issue-rate peak measured with tools/dmma_bench (profiles/)
+            peak = max(fp64_peak, dmma_peak)
+            roof = {"bound": "tensor", "kernel": "trigemm_kernel (FP64 DMMA)", "achieved": fp64_equiv, "peak": peak, "unit": "TFLOP/s",
+                    "frac": fp64_equiv / peak, "traffic": traffic, "ms_per_launch": per_launch_ms, "launches_timed": tri_n,
+                    "algorithmic_flops_per_launch": flops,
+                    "peak_source": f"fp64 is not in MEASURED_PEAKS.json: max(cuBLAS DGEMM 6144^3 measured live = {fp64_peak:.1f} TF/s, "
+                                   f"DMMA.8x8x4 issue-rate microbenchmark tools/dmma_bench = {dmma_peak} TF/s)",
+                    "share_of_sweep": share}
         if world == 1 and not args.no_cpu_baseline:
             cores = blas_threads()
             v, _, cfit = cpu_reference_run(2, 1, args.ref_sample)
@@ -333,7 +360,7 @@ def run_gpu_arm(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(cands, world), "fit_ms": fit_ms,
+                "data": "synthetic", "config": dict(workload_config(cands, world), tensor_path=eng.acquire_path), "fit_ms": fit_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "PointSelector.update_surrogate() + expected_improvement() with host numpy buffers", "candidates_per_step_per_gpu": e2e_cands,
                         "steps": e2e_steps},
@@ -355,6 +382,7 @@ def main():
     ap.add_argument("--e2e-cands", type=int, default=1 << 20)
     ap.add_argument("--ref-sample", type=int, default=8192, help="candidates per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default=None, choices=["i8", "fp64"], help="tensor path of the acquisition product (default: library default, i8)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3          # timing rule: at least 3 warm-up steps
