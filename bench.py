@@ -154,7 +154,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "fit_ms": fit_ms, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(cands, gpus):
@@ -199,7 +199,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BOGP_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        if "BOGP_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["BOGP_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     eng = GPEngine(local)
     if args.path:
@@ -366,12 +367,31 @@ def run_gpu_arm(args):
                         "steps": e2e_steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
                 "selected": {"score": last[0], "flat_index": last[1]}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything that libraries print to stdout (e.g. NCCL's version banner) goes to stderr; the one
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
