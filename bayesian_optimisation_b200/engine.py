@@ -186,6 +186,8 @@ class GPEngine:
         n, dim = dx.shape
         if dl.numel() != dim:
             raise ValueError(f"{dl.numel()} length scales for {dim} features")
+        if dim > _lib.BOGP_MAX_DIM:
+            raise ValueError(f"{dim} features; the kernels support at most {_lib.BOGP_MAX_DIM}")
         nbytes = self.lib.bogp_fit_workspace_bytes(n, dim)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         h = C.c_void_p()

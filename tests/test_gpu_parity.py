@@ -339,3 +339,110 @@ def test_point_selector_dropin_replays_the_reference_closed_loop():
             ps2.feature_domain, ps2.predicted_axes, ps2.length_scales = list(c["feature_domain"]), c["axes"], c["length_scales"]
             ps2.update_surrogate()
             np.testing.assert_array_equal(ps2.lower_confidence_bound(), c["index"])
+
+
+# ------------------------------------------------------------------ BASELINE.json shapes
+def test_baseline_config_n4096_d8_slice_matches_oracle_and_shards(eng):
+    """configs[2] shapes (N=4096, d=8, 10^8-point grid): a slice against the numpy oracle, plus the
+    size-independent properties on a larger slice (8-way sharding == single sweep, EI winner stable)."""
+    from bayesian_optimisation_b200.engine import ACQ_EI, CandidateGrid
+    from bayesian_optimisation_b200.sharding import reduce_pairs, shard_range
+    e = _consts()
+    X, y, ell = o.synthetic_problem(4096, 8)
+    axes = [np.linspace(0, 1, 10)] * 8
+    grid = CandidateGrid(axes)
+    assert grid.size == 10 ** 8
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    start = 31_415_926
+    res = eng.acquire(fit, grid, start, start + 6000, outputs=True)
+    P = o.grid_points(axes, start, start + 6000)
+    mu_ref, var_ref = o.posterior_diag(X, y, P, ell, chunk=1024, return_var=True)
+    cond = cond_of(X, ell, e.JITTER_POSTERIOR)
+    print(f"cond(K) = {cond:.3g}")
+    np.testing.assert_allclose(res.mu.cpu().numpy(), mu_ref, rtol=RTOL, atol=RTOL * np.abs(mu_ref).max())
+    assert_var_close(res.sigma.cpu().numpy() ** 2, var_ref, cond)
+    acq_ref = o.lcb(mu_ref, np.sqrt(np.abs(var_ref)))
+    assert res.best_index == start + int(np.flatnonzero(acq_ref == acq_ref.max())[0])
+    nl = eng.nlml_batched(X, y, ell.reshape(1, -1)).cpu().numpy()[0]
+    ref = o.nlml(X, y, ell, stable=True)
+    assert abs(nl - ref) <= RTOL * abs(ref)
+    # properties on 2^17 candidates
+    fb = float(y.min())
+    b0, count = 50_000_000, 1 << 17
+    full = eng.acquire(fit, grid, b0, b0 + count, kind=ACQ_EI, f_best=fb, outputs=True)
+    parts, pairs = [], []
+    for r in range(8):
+        b, en = shard_range(count, r, 8)
+        part = eng.acquire(fit, grid, b0 + b, b0 + en, kind=ACQ_EI, f_best=fb, outputs=True, chunk=4096)
+        parts.append(part.acq.cpu().numpy())
+        pairs.append((part.best_score, part.best_index))
+    np.testing.assert_array_equal(np.concatenate(parts), full.acq.cpu().numpy())
+    assert reduce_pairs(pairs) == (full.best_score, full.best_index)
+
+
+def test_baseline_config_n16384_d10_properties(eng):
+    """configs[4] shapes (N=16384, d=10, 8^10-point grid): the fit must succeed and the two tensor paths,
+    grid vs explicit candidates and chunkings must agree (the oracle would need a 16384^3 CPU inverse)."""
+    from bayesian_optimisation_b200.engine import CandidateGrid
+    e = _consts()
+    X, y, ell = o.synthetic_problem(16384, 10)
+    axes = [np.linspace(0, 1, 8)] * 10
+    grid = CandidateGrid(axes)
+    assert grid.size == 8 ** 10
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    assert np.isfinite(fit.nlml)
+    start, count = 777_000_000, 3000
+    a = eng.acquire(fit, grid, start, start + count, outputs=True, chunk=1024)
+    b = eng.acquire(fit, o.grid_points(axes, start, start + count), outputs=True, chunk=4096)
+    np.testing.assert_array_equal(a.sigma.cpu().numpy(), b.sigma.cpu().numpy())
+    np.testing.assert_array_equal(a.mu.cpu().numpy(), b.mu.cpu().numpy())
+    assert a.best_index - start == b.best_index
+    other = "fp64" if eng.acquire_path == "i8" else "i8"
+    eng.set_acquire_path(other)
+    c = eng.acquire(fit, grid, start, start + count, outputs=True)
+    np.testing.assert_allclose(c.sigma.cpu().numpy() ** 2, a.sigma.cpu().numpy() ** 2, rtol=0, atol=5e-12)
+    assert c.best_index == a.best_index
+    # against a direct fp64 evaluation with the device factor: sigma^2 = prior - |L^-1 k|^2
+    import torch
+    Lt = torch.tril(fit.chol()[:16384, :16384])
+    Pd = torch.from_numpy(o.grid_points(axes, start, start + 64)).cuda()
+    Xd = torch.from_numpy(X).cuda()
+    ks = torch.exp(-0.5 * (((Pd[:, None, :] - Xd[None, :, :]) ** 2) / torch.from_numpy(ell ** 2).cuda()).sum(-1))   # (64, N)
+    v = torch.linalg.solve_triangular(Lt, ks.T.contiguous(), upper=False)
+    var = e.PRIOR_DIAG - (v * v).sum(0)
+    np.testing.assert_allclose(a.sigma.cpu().numpy()[:64] ** 2, var.cpu().numpy(), rtol=1e-9, atol=5e-11)
+
+
+# ------------------------------------------------------------------ edge shapes
+@pytest.mark.parametrize("n,d,c", [(1, 1, 1), (1, 2, 63), (2, 16, 65), (3, 5, 64), (257, 3, 129), (40, 7, 1000)])
+def test_edge_shapes_match_oracle(eng, n, d, c):
+    e = _consts()
+    rng = np.random.default_rng(n * 100 + d)
+    X, y, P = rng.random((n, d)), rng.standard_normal(n), rng.random((c, d))
+    ell = 0.3 + rng.random(d)
+    mu_ref, var_ref = o.posterior_diag(X, y, P, ell, return_var=True)
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    quirk = X.shape == P.shape        # the reference's shape-equality jitter on k(X, P) (point_selector.py:173-177)
+    res = eng.acquire(fit, P, outputs=True, cross_jitter=e.JITTER_LML if quirk else 0.0)
+    np.testing.assert_allclose(res.mu.cpu().numpy(), mu_ref, rtol=RTOL, atol=RTOL * max(1e-300, np.abs(mu_ref).max()))
+    assert_var_close(res.sigma.cpu().numpy() ** 2, var_ref, cond_of(X, ell, e.JITTER_POSTERIOR))
+    acq = o.lcb(mu_ref, np.sqrt(np.abs(var_ref)))
+    assert res.best_index == int(np.flatnonzero(acq == acq.max())[0])
+
+
+def test_bad_arguments_are_rejected(eng):
+    from bayesian_optimisation_b200.engine import CandidateGrid
+    from bayesian_optimisation_b200 import BogpError
+    e = _consts()
+    X, y, ell = o.synthetic_problem(10, 3, seed=1)
+    with pytest.raises(ValueError):
+        eng.fit(X, y, ell[:2])
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    with pytest.raises(ValueError):
+        eng.acquire(fit, np.zeros((5, 2)))
+    with pytest.raises(ValueError):
+        eng.acquire(fit, CandidateGrid([np.linspace(0, 1, 3)] * 2))
+    with pytest.raises(BogpError):
+        eng.acquire(fit, np.zeros((5, 3)), 3, 9)          # range beyond the candidate count
+    with pytest.raises(ValueError):
+        eng.fit(np.zeros((4, 17)), np.zeros(4), np.ones(17))   # more than BOGP_MAX_DIM features
