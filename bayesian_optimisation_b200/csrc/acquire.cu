@@ -378,22 +378,73 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
     init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
 
     const bool use_i8 = ctx->acquire_path == BOGP_PATH_INT8_TCGEN05;
-    for (int64_t c0 = c_begin; c0 < c_end; c0 += S) {
-        const int64_t cur = (c_end - c0 < S) ? (c_end - c0) : S;
-        const int nct = (int)((cur + kAcqBN - 1) / kAcqBN);
-        int nIq;
-        if (use_i8) {
+    auto finish_chunk = [&](int64_t c0, int64_t cur, int64_t Sb, const double* qp, const double* mp, int nIq) -> int {
+        const int nfb = (int)((cur + 255) / 256);
+        if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }
+        const int64_t o = c0 - c_begin;
+        FinalArgs fa{qp, mp, d_mu_out ? d_mu_out + o : nullptr, d_sigma_out ? d_sigma_out + o : nullptr,
+                     d_acq_out ? d_acq_out + o : nullptr, ctx->d_block_score, ctx->d_block_index, nan_flag,
+                     c0, cur, Sb, nIq, nI, kind, explore, f_best, prior_diag};
+        BOGP_PROFILED(ctx, BOGP_PROF_FINALIZE, (finalize_kernel<<<nfb, 256, 0, st>>>(fa))); BOGP_LAUNCH_CHECK(ctx);
+        BOGP_PROFILED(ctx, BOGP_PROF_MERGE, (merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti))); BOGP_LAUNCH_CHECK(ctx);
+        return BOGP_OK;
+    };
+    if (use_i8) {
+        // INT8 path.  The panel kernel (FP64/INT pipes) and the tensor-core kernel use different
+        // pipes and fit on one SM together, so with two buffer sets the panel of chunk s+1 is built
+        // on a second stream while chunk s is on the tensor cores.
+        const int64_t total = c_end - c_begin;
+        const bool overlap = !ctx->profile && total > S / 2 && S >= 4 * kAcqBN;
+        const int nbuf = overlap ? 2 : 1;
+        const int64_t Sb = overlap ? (S / 2) / kAcqBN * kAcqBN : S;
+        const AcqLayout lb = acq_layout(n_pad, Sb);
+        if ((size_t)nbuf * lb.total > workspace_bytes) { set_error("bogp_acquire: workspace too small"); return BOGP_ERR_WORKSPACE; }
+        auto make_chunk = [&](int64_t c0, int b) {
             AcqChunk a{};
+            char* bb = base + (size_t)b * lb.total;
             a.points = cd.points; a.axes = cd.axes; a.cross_jitter = cd.cross_jitter;
             for (int k = 0; k < BOGP_MAX_DIM; k++) { a.len[k] = cd.len[k]; a.off[k] = cd.off[k]; }
             a.x_pad = fit_xpad(fit); a.inv_ell2 = fit_inv_ell2(fit); a.alpha = fit_alpha(fit);
             a.wp = fit_wp(fit); a.wq = fit_wq(fit); a.wscale = fit_wscale(fit);
-            a.panel = panel; a.qpart = qpart; a.mupart = mupart;
-            a.c0 = c0; a.c_end = c_end; a.cur = cur; a.S = S; a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
-            int rc = launch_acquire_chunk_i8(ctx, a);
+            a.panel = bb + lb.panel; a.qpart = (double*)(bb + lb.qpart); a.mupart = (double*)(bb + lb.mupart);
+            a.c0 = c0; a.c_end = c_end; a.cur = (c_end - c0 < Sb) ? (c_end - c0) : Sb; a.S = Sb;
+            a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
+            return a;
+        };
+        cudaStream_t ps = overlap ? ctx->aux_stream : st;
+        if (overlap) {
+            BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
+            BOGP_CUDA_CHECK(cudaStreamWaitEvent(ps, ctx->ev_fork, 0));
+        }
+        const int64_t nchunks = (total + Sb - 1) / Sb;
+        int rc = launch_panel_i8(ctx, make_chunk(c_begin, 0), ps);
+        if (rc) return rc;
+        if (overlap) BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_panel[0], ps));
+        for (int64_t s = 0; s < nchunks; s++) {
+            const int b = (int)(s % nbuf);
+            if (overlap && s + 1 < nchunks) {          // next panel into the other buffer set
+                const int nb = (int)((s + 1) % 2);
+                if (s >= 1) BOGP_CUDA_CHECK(cudaStreamWaitEvent(ps, ctx->ev_done[nb], 0));
+                rc = launch_panel_i8(ctx, make_chunk(c_begin + (s + 1) * Sb, nb), ps);
+                if (rc) return rc;
+                BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_panel[nb], ps));
+            }
+            const AcqChunk a = make_chunk(c_begin + s * Sb, b);
+            if (overlap) BOGP_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_panel[b], 0));
+            rc = launch_trigemm_i8(ctx, a, st);
             if (rc) return rc;
-            nIq = (int)(n_pad / 128);
-        } else {
+            rc = finish_chunk(a.c0, a.cur, Sb, a.qpart, a.mupart, (int)(n_pad / 128));
+            if (rc) return rc;
+            if (overlap) BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_done[b], st));
+            if (!overlap && s + 1 < nchunks) {
+                rc = launch_panel_i8(ctx, make_chunk(c_begin + (s + 1) * Sb, 0), ps);
+                if (rc) return rc;
+            }
+        }
+    } else {
+        for (int64_t c0 = c_begin; c0 < c_end; c0 += S) {
+            const int64_t cur = (c_end - c0 < S) ? (c_end - c0) : S;
+            const int nct = (int)((cur + kAcqBN - 1) / kAcqBN);
             PanelArgs pa{cd, fit_xpad(fit), fit_inv_ell2(fit), fit_alpha(fit), panel, mupart, c0, c_end, S, (int)fit_n(fit), (int)n_pad, dim};
 #define BOGP_PANEL(D) BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_kernel<D><<<dim3(nct, nI), 256, 0, st>>>(pa)))
             if (dim <= 2) BOGP_PANEL(2); else if (dim <= 4) BOGP_PANEL(4); else if (dim <= 6) BOGP_PANEL(6);
@@ -403,16 +454,9 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
             BOGP_LAUNCH_CHECK(ctx);
             TriArgs ta{fit_wp(fit), panel, qpart, nI, nct, (int)n_pad, S};
             BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_kernel<<<nI * nct, 288, kTriSmem, st>>>(ta))); BOGP_LAUNCH_CHECK(ctx);
-            nIq = nI;
+            int rc = finish_chunk(c0, cur, S, qpart, mupart, nI);
+            if (rc) return rc;
         }
-        const int nfb = (int)((cur + 255) / 256);
-        if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }
-        const int64_t o = c0 - c_begin;
-        FinalArgs fa{qpart, mupart, d_mu_out ? d_mu_out + o : nullptr, d_sigma_out ? d_sigma_out + o : nullptr,
-                     d_acq_out ? d_acq_out + o : nullptr, ctx->d_block_score, ctx->d_block_index, nan_flag,
-                     c0, cur, S, nIq, nI, kind, explore, f_best, prior_diag};
-        BOGP_PROFILED(ctx, BOGP_PROF_FINALIZE, (finalize_kernel<<<nfb, 256, 0, st>>>(fa))); BOGP_LAUNCH_CHECK(ctx);
-        BOGP_PROFILED(ctx, BOGP_PROF_MERGE, (merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti))); BOGP_LAUNCH_CHECK(ctx);
     }
     if (h_best_score || h_best_index) {
         double hs; long long hi; int hn;

@@ -416,12 +416,7 @@ int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp,
 
 size_t i8_panel_bytes(int64_t n_pad, int64_t S) { return (size_t)n_pad * S * kI8Slices; }
 
-int launch_acquire_chunk_i8(bogp_ctx* ctx, const AcqChunk& a) {
-    static bool configured = false;
-    if (!configured) {
-        BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kI8Smem));
-        configured = true;
-    }
+int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
     const int nct = (int)((a.cur + kI8BN - 1) / kI8BN);
     PanelI8Args pa{};
     pa.cand.points = a.points; pa.cand.axes = a.axes; pa.cand.cross_jitter = a.cross_jitter;
@@ -430,22 +425,33 @@ int launch_acquire_chunk_i8(bogp_ctx* ctx, const AcqChunk& a) {
     pa.c0 = a.c0; pa.c_end = a.c_end; pa.S = a.S; pa.n = a.n; pa.n_pad = a.n_pad; pa.dim = a.dim;
     const bool ub = a.n_pad <= 8192;      // unsigned panel digits while the int32 level sums cannot overflow
     const dim3 pgrid(nct, a.n_pad / kAcqBM);
-#define BOGP_PANEL_I8(D)                                                                                              \
-    do {                                                                                                              \
-        if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true><<<pgrid, 256, 0, ctx->stream>>>(pa))); }  \
-        else    { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false><<<pgrid, 256, 0, ctx->stream>>>(pa))); } \
+#define BOGP_PANEL_I8(D)                                                                                          \
+    do {                                                                                                          \
+        if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true><<<pgrid, 256, 0, stream>>>(pa))); }   \
+        else    { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false><<<pgrid, 256, 0, stream>>>(pa))); }  \
     } while (0)
     if (a.dim <= 2) BOGP_PANEL_I8(2); else if (a.dim <= 4) BOGP_PANEL_I8(4); else if (a.dim <= 6) BOGP_PANEL_I8(6);
     else if (a.dim <= 8) BOGP_PANEL_I8(8); else if (a.dim <= 10) BOGP_PANEL_I8(10); else if (a.dim <= 12) BOGP_PANEL_I8(12);
     else BOGP_PANEL_I8(16);
 #undef BOGP_PANEL_I8
     BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kI8Smem));
+        configured = true;
+    }
+    const int nct = (int)((a.cur + kI8BN - 1) / kI8BN);
+    const bool ub = a.n_pad <= 8192;
     const int nI = a.n_pad / kI8BM;
     int group = (int)((32u << 20) / ((size_t)(a.n_pad / kI8KB) * kI8BTile));     // ~32 MB of panel per group
     group = group < 1 ? 1 : (group > 64 ? 64 : group);
     const int ngroups = (nct + group - 1) / group;
     TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S, ub ? 0 : 1, group};
-    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<ngroups * nI * group, 192, kI8Smem, ctx->stream>>>(ta)));
+    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<ngroups * nI * group, 192, kI8Smem, stream>>>(ta)));
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }

@@ -47,6 +47,17 @@ extern "C" int bogp_create(int device, bogp_ctx** out) {
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_block_index, kMaxReduceBlocks * sizeof(long long)));
     BOGP_CUDA_CHECK(cudaMemset(c->d_scalars, 0, 64 * sizeof(double)));
     BOGP_CUDA_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+    {   // the panel stream gets the highest priority: its CTAs fit next to a running tensor-core CTA, and the
+        // work distributor only interleaves a second kernel ahead of pending CTAs if it has priority
+        int lo = 0, hi = 0;
+        BOGP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BOGP_CUDA_CHECK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    }
+    BOGP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        BOGP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_panel[i], cudaEventDisableTiming));
+        BOGP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
     BOGP_CUDA_CHECK(cudaEventCreate(&c->ev[0]));
     BOGP_CUDA_CHECK(cudaEventCreate(&c->ev[1]));
     *out = c;
@@ -77,6 +88,9 @@ extern "C" int bogp_profile_read(const bogp_ctx* ctx, int kernel_id, double* ms_
 extern "C" void bogp_destroy(bogp_ctx* ctx) {
     if (!ctx) return;
     cudaEventDestroy(ctx->ev[0]); cudaEventDestroy(ctx->ev[1]);
+    cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_panel[i]); cudaEventDestroy(ctx->ev_done[i]); }
+    cudaStreamDestroy(ctx->aux_stream);
     cudaFree(ctx->d_scalars); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_score); cudaFree(ctx->d_block_index);
     delete ctx;
 }

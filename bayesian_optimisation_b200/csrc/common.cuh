@@ -72,6 +72,9 @@ struct bogp_ctx {
     long long*   d_block_index; // kMaxBlocks
     double*      h_pinned;      // 64 doubles pinned host staging
     // optional per-kernel timing of the acquisition sweep (bogp_profile): CUDA events on the launching stream
+    // second stream + events: the k_* panel of chunk s+1 is built while chunk s is on the tensor cores
+    cudaStream_t aux_stream;
+    cudaEvent_t  ev_fork, ev_panel[2], ev_done[2];
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
     cudaEvent_t  ev[2];

@@ -30,7 +30,8 @@ struct AcqChunk {
     int64_t c0, c_end, cur, S;
     int n, n_pad, dim;
 };
-int launch_acquire_chunk_i8(bogp_ctx* ctx, const AcqChunk& a);
+int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream);
+int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream);
 size_t i8_wq_bytes(int64_t n_pad);
 size_t i8_panel_bytes(int64_t n_pad, int64_t S);
 int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp, double* d_wscale, uint8_t* d_wq);
