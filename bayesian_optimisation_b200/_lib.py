@@ -54,6 +54,8 @@ SIGNATURES = {
     "bogp_kernel_matrix": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _dbl, _vp, _i64]),
     "bogp_fit_workspace_bytes": (_sz, [_i64, _i32]),
     "bogp_fit_create": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _dbl, _vp, _sz, C.POINTER(_vp), C.POINTER(_dbl)]),
+    "bogp_fit_enqueue": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _dbl, _vp, _sz, C.POINTER(_vp)]),
+    "bogp_fit_status": (_i32, [_vp, C.POINTER(_dbl)]),
     "bogp_fit_destroy": (None, [_vp]),
     "bogp_fit_n_pad": (_i64, [_vp]),
     "bogp_fit_chol": (_vp, [_vp]),

@@ -52,9 +52,16 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
     const int wm = warp >> 1, wn = warp & 1;
     constexpr int WM = BM / 4, WN = BN / 2, MI = WM / 8, NI = WN / 8;
 
-    // row blocks whose k range grows with m are scheduled heaviest-first
-    const int by = (KR == K_LE_M) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-    const int m0 = by * BM, n0 = blockIdx.x * BN;
+    // Tiles with a restricted k range are scheduled heaviest-first: K_LE_M grows with m (row blocks in
+    // reverse order), K_GE_N shrinks with n (the column block becomes the slow grid index, ascending).
+    int bx = (int)blockIdx.x, by = (int)blockIdx.y;
+    if (KR == K_LE_M) by = (int)(gridDim.y - 1 - blockIdx.y);
+    if (KR == K_GE_N) {
+        const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+        by = lin % (int)gridDim.y;
+        bx = lin / (int)gridDim.y;
+    }
+    const int m0 = by * BM, n0 = bx * BN;
     if (g.lower_only && n0 > m0 + BM - 1) return;
 
     const int zi = g.inner > 1 ? (int)(blockIdx.z % g.inner) : (g.inner == 1 ? 0 : (int)blockIdx.z);
@@ -181,6 +188,7 @@ inline int launch_gemm(bogp_ctx* ctx, const GemmArgs& g, int batch) {
     constexpr size_t smem = GemmSmem<BM, BN>::bytes;
     if (!configured) {
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return BOGP_OK;

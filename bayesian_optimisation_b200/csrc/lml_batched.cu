@@ -264,8 +264,8 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
         const int rb = (int)((r - r0 < 32768) ? (r - r0) : 32768);
         double* Ab = A + r0 * mat; double* Wb = W + r0 * mat;
         rc = launch_gram(ctx, x_pad, np, n, x_pad, np, n, dim, il + r0 * dim, jitter, Ab, np, true, rb, mat); if (rc) return rc;
-        rc = cholesky_blocked(ctx, Ab, np, np, mat, Wb, np, mat, logdet + r0, info + r0, rb); if (rc) return rc;
-        rc = trtri_recursive(ctx, Ab, np, mat, Wb, np, mat, T + r0 * l.tper, (int64_t)l.tper, np, rb); if (rc) return rc;
+        rc = cholesky_blocked(ctx, Ab, np, np, mat, Wb, np, mat, logdet + r0, info + r0, rb, T + r0 * l.tper, (int64_t)l.tper); if (rc) return rc;
+        rc = trtri_recursive(ctx, Ab, np, mat, Wb, np, mat, T + r0 * l.tper, (int64_t)l.tper, np, rb, 256); if (rc) return rc;
         rc = launch_alpha(ctx, Wb, np, mat, y_pad, v + r0 * np, alpha + r0 * np, (int)np, rb); if (rc) return rc;
         if (d_grad_out) {
             GemmArgs k{};   // Kinv = W^T W (lower part) into A (L is dead)

@@ -87,6 +87,13 @@ size_t bogp_fit_workspace_bytes(int64_t n, int dim);
 int  bogp_fit_create(bogp_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int dim,
                      const double* d_ell, double jitter, void* d_workspace, size_t workspace_bytes,
                      bogp_fit** out, double* h_nlml_out);
+/* The same in two steps: bogp_fit_enqueue only enqueues device work (no synchronisation, so the
+ * host may record it into a CUDA graph and replay it); bogp_fit_status synchronises and reports
+ * BOGP_ERR_NOT_POSDEF / the nlml of the most recent execution.                                    */
+int  bogp_fit_enqueue(bogp_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int dim,
+                      const double* d_ell, double jitter, void* d_workspace, size_t workspace_bytes,
+                      bogp_fit** out);
+int  bogp_fit_status(bogp_fit* fit, double* h_nlml_out);
 void bogp_fit_destroy(bogp_fit* fit);
 /* inspection (device pointers into the workspace; n_pad = n rounded up to 256) */
 int64_t       bogp_fit_n_pad(const bogp_fit* fit);

@@ -446,3 +446,44 @@ def test_bad_arguments_are_rejected(eng):
         eng.acquire(fit, np.zeros((5, 3)), 3, 9)          # range beyond the candidate count
     with pytest.raises(ValueError):
         eng.fit(np.zeros((4, 17)), np.zeros(4), np.ones(17))   # more than BOGP_MAX_DIM features
+
+
+def test_fit_enqueue_is_graph_capturable(eng):
+    """bogp_fit_enqueue issues device work only, so the whole fit (~290 launches on two streams with
+    look-ahead) can be recorded once into a CUDA graph and replayed; the replay reproduces the eager
+    nlml bit for bit."""
+    import ctypes as C
+    import torch
+    from bayesian_optimisation_b200 import _lib
+    e = _consts()
+    X, y, ell = o.synthetic_problem(1024, 6, seed=4)
+    dX, dy, dl = eng.to_device(X), eng.to_device(y), eng.to_device(ell)
+    nbytes = eng.lib.bogp_fit_workspace_bytes(1024, 6)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+
+    def enqueue():
+        eng._sync_stream()
+        h = C.c_void_p()
+        _lib.check(eng.lib.bogp_fit_enqueue(eng._ctx, dX.data_ptr(), dy.data_ptr(), 1024, 6, dl.data_ptr(), e.JITTER_LML,
+                                            ws.data_ptr(), nbytes, C.byref(h)))
+        return h
+
+    h = enqueue()
+    eager = C.c_double()
+    _lib.check(eng.lib.bogp_fit_status(h, C.byref(eager)))
+    eng.lib.bogp_fit_destroy(h)
+    ref = o.nlml(X, y, ell)
+    assert abs(eager.value - ref) <= RTOL * abs(ref)
+    g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            hg = enqueue()
+    ws.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    eng._sync_stream()
+    replay = C.c_double()
+    _lib.check(eng.lib.bogp_fit_status(hg, C.byref(replay)))
+    eng.lib.bogp_fit_destroy(hg)
+    assert replay.value == eager.value

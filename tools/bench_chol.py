@@ -11,6 +11,7 @@ for n in [int(a) for a in sys.argv[1].split(",")]:
     X, y, ell = o.synthetic_problem(n, 8, seed=1)
     K = torch.from_numpy(o.kernel_rbf(X, X, ell)).cuda()
     a = K.clone(); linv = torch.zeros_like(a)
+    X8 = X
     scal = torch.zeros(1, dtype=torch.float64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
     def run():
         _lib.check(eng.lib.bogp_cholesky(eng._ctx, a.data_ptr(), n, n, linv.data_ptr(), scal.data_ptr(), info.data_ptr()))
@@ -26,3 +27,9 @@ for n in [int(a) for a in sys.argv[1].split(",")]:
     a.copy_(K); run(); torch.cuda.synchronize()
     print({k: (round(v[0]*1e3/max(1,v[1]),1), v[1]) for k, v in eng.profile_read().items() if v[1]}, "(avg us, launches)")
     eng.profile(False)
+
+    # full fit with per-kernel timing
+    eng.profile(True)
+    f = eng.fit(X, y, ell); torch.cuda.synchronize()
+    print("fit:", {k: (round(v[0]*1e3/max(1,v[1]),1), v[1], round(v[0],2)) for k, v in eng.profile_read().items() if v[1]}, "(avg us, launches, total ms)")
+    eng.profile(False); f.close()
