@@ -30,7 +30,7 @@ struct GemmArgs {
 };
 
 constexpr int GK = 16;          // k extent per stage
-constexpr int GSTAGES = 3;
+constexpr int GSTAGES = 4;
 constexpr int GPADK = GK + 4;   // row stride (doubles) of an [rows][k] tile: conflict-free fragment loads
 
 template <int BM, int BN>

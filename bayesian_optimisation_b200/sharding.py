@@ -57,6 +57,34 @@ def allreduce_maxloc(score: float, index: int, device=None, group=None) -> Tuple
     return reduce_pairs(pairs)
 
 
+def allreduce_minloc(value: float, index: int, device=None, group=None) -> Tuple[float, int]:
+    """(smallest value, then smallest index) across ranks -- the restart that wins a sharded
+    length-scale fit.  Same 16-byte exchange as `allreduce_maxloc`."""
+    s, i = allreduce_maxloc(-float(value) if value == value else float("nan"), index, device=device, group=group)
+    return -s, i
+
+
+def sharded_nlml_argmin(engine, x, y, ells, rank: int, world: int, jitter=None, group=None):
+    """Multi-restart length-scale selection across GPUs: rank r evaluates restarts r, r+G, ... with one
+    batched launch (K3), rounds to float32 like the reference's table (point_selector.py:126) and the
+    ranks agree on the first minimum (lowest restart id among ties, point_selector.py:141).
+    Returns (nlml_float32, restart_id, local_table)."""
+    import numpy as np
+    ids = np.arange(rank, len(ells), world)
+    kw = {} if jitter is None else {"jitter": jitter}
+    if len(ids):
+        table = engine.nlml_batched(x, y, np.asarray(ells)[ids], **kw).cpu().numpy().astype(np.float32)
+        k = int(np.flatnonzero(table == np.amin(table))[0]) if not np.isnan(table).any() else 0
+        val, idx = float(table[k]), int(ids[k])
+        if np.isnan(table).any():
+            val = float("nan")
+    else:
+        table, val, idx = np.zeros(0, np.float32), float("inf"), NO_INDEX
+    use_dev = dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+    gv, gi = allreduce_minloc(val, idx, device=engine.device if use_dev else None, group=group)
+    return gv, gi, table
+
+
 def sharded_acquire(engine, fit, candidates, c_total: int, rank: int, world: int, group=None, **kw):
     """Score this rank's slice on its GPU and reduce.  Returns (score, index, local AcquireResult)."""
     b, e = shard_range(c_total, rank, world)

@@ -120,6 +120,16 @@ axes = [np.linspace(0, 1, 6)] * 3
 P = o.candidate_grid(axes)
 b, e = shard_range(len(P), rank, world)
 mu, sig = o.posterior_diag(X, y, P[b:e], ell)            # the oracle stands in for the GPU scorer here
+# restart sharding (sharded_nlml_argmin) with a CPU stand-in for the batched GPU kernel
+class _CpuEngine:
+    device = None
+    def nlml_batched(self, x, y, ells, **kw):
+        return torch.tensor([o.nlml(x, y, e) for e in ells], dtype=torch.float64)
+from bayesian_optimisation_b200.sharding import sharded_nlml_argmin
+ells = np.exp(np.random.default_rng(5).uniform(np.log(0.2), np.log(1.0), (13, 3)))
+gv, gi, _ = sharded_nlml_argmin(_CpuEngine(), X, y, ells, rank, world)
+full_table = np.array([o.nlml(X, y, e) for e in ells]).astype(np.float32)
+assert gi == int(np.flatnonzero(full_table == full_table.min())[0]) and np.float32(gv) == full_table.min(), (gi, gv)
 acq = o.lcb(mu, sig)
 acq[:] = np.round(acq, 1)                                 # force exact ties across ranks
 li = int(np.flatnonzero(acq == acq.max())[0])
