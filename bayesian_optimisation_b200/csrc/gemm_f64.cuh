@@ -29,15 +29,17 @@ struct GemmArgs {
     int lower_only;     // only tiles / elements with row >= col are produced (SYRK)
 };
 
-constexpr int GK = 16;          // k extent per stage
-constexpr int GSTAGES = 4;
-constexpr int GPADK = GK + 4;   // row stride (doubles) of an [rows][k] tile: conflict-free fragment loads
+constexpr int GK = 32;          // k extent per stage
+constexpr int GPADK = GK + 4;   // row stride (doubles) of an [rows][k] tile: stride = 4 (mod 16) -> conflict-free fragment loads
 
 template <int BM, int BN>
 struct GemmSmem {
     static constexpr int kAStage = (BM * GPADK > GK * (BM + 4)) ? BM * GPADK : GK * (BM + 4);
     static constexpr int kBStage = (BN * GPADK > GK * (BN + 4)) ? BN * GPADK : GK * (BN + 4);
-    static constexpr size_t bytes = size_t(GSTAGES) * (kAStage + kBStage) * sizeof(double);
+    static constexpr size_t kStageBytes = size_t(kAStage + kBStage) * sizeof(double);
+    // as many stages as fit into the 227 KB of one CTA, at most 4, at least 2
+    static constexpr int kStages = (4 * kStageBytes <= 227 * 1024) ? 4 : ((3 * kStageBytes <= 227 * 1024) ? 3 : 2);
+    static constexpr size_t bytes = size_t(kStages) * kStageBytes;
 };
 
 // 256 threads = 8 warps arranged 4 (m) x 2 (n); warp tile (BM/4) x (BN/2).
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
     using S = GemmSmem<BM, BN>;
     double* sA = smem;
+    constexpr int GSTAGES = S::kStages;
     double* sB = smem + GSTAGES * S::kAStage;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -131,46 +131,73 @@ __global__ void __launch_bounds__(256) nlml_small_kernel(SmallArgs g) {
 // ------------------------------------------------------------------------------------------------
 // large path pieces
 // ------------------------------------------------------------------------------------------------
-// gpart[r][rowblock][k] = sum over rows of the block, cols j < i, of (alpha_i alpha_j - Kinv_ij) k_ij (x_ik-x_jk)^2
+// gpart[r][tile][k] = sum over the pairs (i > j) of one 64x64 tile of
+//   (alpha_i alpha_j - Kinv_ij) k_ij (x_ik - x_jk)^2.
+// grid (lower tiles, restarts); 256 threads, 4x4 pairs per thread, coordinates staged in shared
+// memory, fixed-order block reduction.
 struct GradArgs {
     const double* x_pad; const double* inv_ell2; const double* alpha; const double* kinv;
-    double* gpart; int n, n_pad, dim, nrb;
+    double* gpart; int n, n_pad, dim, ntiles;
 };
 
 __global__ void __launch_bounds__(256) grad_contract_kernel(GradArgs g) {
-    __shared__ double red[256 * BOGP_MAX_DIM];
-    __shared__ double il[BOGP_MAX_DIM];
-    const int tid = threadIdx.x, rb = blockIdx.x, dim = g.dim;
+    __shared__ double xi[BOGP_MAX_DIM][64], xj[BOGP_MAX_DIM][64];
+    __shared__ double ai[64], aj[64], il[BOGP_MAX_DIM];
+    __shared__ double red[8][BOGP_MAX_DIM];
+    const int tid = threadIdx.x, dim = g.dim;
     const int64_t r = blockIdx.y;
+    // tile index -> (bi, bj), bi >= bj
+    int bi = 0, t = blockIdx.x;
+    while (t > bi) { t -= bi + 1; bi++; }
+    const int bj = t;
     const double* kinv = g.kinv + r * (int64_t)g.n_pad * g.n_pad;
     const double* al = g.alpha + r * (int64_t)g.n_pad;
+    for (int e = tid; e < 64 * dim; e += 256) {
+        const int p = e / dim, k = e % dim;
+        xi[k][p] = g.x_pad[(int64_t)(bi * 64 + p) * dim + k];
+        xj[k][p] = g.x_pad[(int64_t)(bj * 64 + p) * dim + k];
+    }
+    if (tid < 64) { ai[tid] = al[bi * 64 + tid]; aj[tid] = al[bj * 64 + tid]; }
     if (tid < dim) il[tid] = g.inv_ell2[r * dim + tid];
     __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
     double acc[BOGP_MAX_DIM];
 #pragma unroll
     for (int k = 0; k < BOGP_MAX_DIM; k++) acc[k] = 0.0;
-    const int i0 = rb * 64, i1 = min(g.n, i0 + 64);
-    for (int i = i0; i < i1; i++) {
-        const double ai = al[i];
-        double xi[BOGP_MAX_DIM];
 #pragma unroll
-        for (int k = 0; k < BOGP_MAX_DIM; k++) xi[k] = k < dim ? g.x_pad[(int64_t)i * dim + k] : 0.0;
-        for (int j = tid; j < i; j += 256) {
+    for (int a = 0; a < 4; a++) {
+        const int li = ty * 4 + a, i = bi * 64 + li;
+        const double2 k01 = *reinterpret_cast<const double2*>(kinv + (int64_t)i * g.n_pad + bj * 64 + tx * 4);
+        const double2 k23 = *reinterpret_cast<const double2*>(kinv + (int64_t)i * g.n_pad + bj * 64 + tx * 4 + 2);
+        const double kv[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int lj = tx * 4 + b, j = bj * 64 + lj;
+            if (j >= i || i >= g.n) continue;                  // strictly lower pairs of real points
             double s = 0.0, d2[BOGP_MAX_DIM];
 #pragma unroll
-            for (int k = 0; k < BOGP_MAX_DIM; k++) if (k < dim) { const double df = xi[k] - g.x_pad[(int64_t)j * dim + k]; d2[k] = df * df; s += d2[k] * il[k]; }
-            const double c = (ai * al[j] - kinv[(int64_t)i * g.n_pad + j]) * exp(-0.5 * s);
+            for (int k = 0; k < BOGP_MAX_DIM; k++)
+                if (k < dim) { const double df = xi[k][li] - xj[k][lj]; d2[k] = df * df; s += d2[k] * il[k]; }
+            const double c = (ai[li] * aj[lj] - kv[b]) * exp(-0.5 * s);
 #pragma unroll
             for (int k = 0; k < BOGP_MAX_DIM; k++) if (k < dim) acc[k] += c * d2[k];
         }
     }
 #pragma unroll
-    for (int k = 0; k < BOGP_MAX_DIM; k++) if (k < dim) red[tid * dim + k] = acc[k];
+    for (int k = 0; k < BOGP_MAX_DIM; k++) {
+        if (k < dim) {                                         // fixed xor tree over the warp, then the 8 warps in order
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0) red[tid >> 5][k] = v;
+        }
+    }
     __syncthreads();
     if (tid < dim) {
         double s = 0.0;
-        for (int t = 0; t < 256; t++) s += red[t * dim + tid];
-        g.gpart[(r * g.nrb + rb) * dim + tid] = s;
+#pragma unroll
+        for (int q = 0; q < 8; q++) s += red[q][tid];
+        g.gpart[(r * g.ntiles + blockIdx.x) * dim + tid] = s;
     }
 }
 
@@ -211,7 +238,7 @@ static LmlLayout lml_layout(int64_t n, int dim, int64_t R, int want_grad) {
     l.x = take(np * dim * 8); l.y = take(np * 8); l.il = take(R * dim * 8);
     l.a = take((size_t)R * np * np * 8); l.w = take((size_t)R * np * np * 8); l.t = take((size_t)R * l.tper * 8);
     l.alpha = take(R * np * 8); l.v = take(R * np * 8); l.logdet = take(R * 8); l.info = take(R * 4);
-    l.gpart = take(want_grad ? (size_t)R * (np / 64) * dim * 8 : 8);
+    l.gpart = take(want_grad ? (size_t)R * ((np / 64) * (np / 64 + 1) / 2) * dim * 8 : 8);
     l.total = off;
     return l;
 }
@@ -272,13 +299,13 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
             k.A = Wb; k.lda = np; k.strideA = mat; k.B = Wb; k.ldb = np; k.strideB = mat; k.C = Ab; k.ldc = np; k.strideC = mat;
             k.M = (int)np; k.N = (int)np; k.K = (int)np; k.alpha = 1.0; k.accumulate = 0; k.lower_only = 1;
             rc = launch_gemm<128, 128, A_KM, B_KN, K_GE_MAXMN>(ctx, k, rb); if (rc) return rc;
-            const int nrb = (int)(np / 64);
-            GradArgs ga{x_pad, il + r0 * dim, alpha + r0 * np, Ab, gpart + r0 * nrb * dim, (int)n, (int)np, dim, nrb};
-            grad_contract_kernel<<<dim3(nrb, rb), 256, 0, st>>>(ga); BOGP_LAUNCH_CHECK(ctx);
+            const int nt = (int)(np / 64), ntiles = nt * (nt + 1) / 2;
+            GradArgs ga{x_pad, il + r0 * dim, alpha + r0 * np, Ab, gpart + r0 * ntiles * dim, (int)n, (int)np, dim, ntiles};
+            grad_contract_kernel<<<dim3(ntiles, rb), 256, 0, st>>>(ga); BOGP_LAUNCH_CHECK(ctx);
         }
     }
     lml_finish_kernel<<<(unsigned)((r + 7) / 8), 256, 0, st>>>(y_pad, alpha, logdet, gpart, d_ell, d_nlml_out, d_grad_out,
-                                                             (int)n, (int)np, dim, (int)(np / 64), r);
+                                                             (int)n, (int)np, dim, (int)((np / 64) * (np / 64 + 1) / 2), r);
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }
