@@ -247,7 +247,8 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
         s.B = tall; s.ldb = lda; s.strideB = strideA;
         s.C = d_a + row0 * (lda + 1); s.ldc = lda; s.strideC = strideA;
         s.M = below; s.N = (int)nextw; s.K = (int)wpan; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
-        BOGP_PROFILED(ctx, 7, (rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, s, batch)));
+        if (batch == 1) { BOGP_PROFILED(ctx, 7, (rc = launch_gemm_tma_nt(ctx, s))); } else rc = 1;
+        if (rc == 1) { BOGP_PROFILED(ctx, 7, (rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, s, batch))); }
         if (rc) return rc;
         if (lookahead && below > nextw) {
             BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_panel[0], ctx->stream));
@@ -260,7 +261,8 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
             r.M = (int)(n - row1); r.N = (int)(n - row1); r.K = (int)wpan; r.alpha = -1.0; r.accumulate = 1; r.lower_only = 1;
             cudaStream_t main_stream = ctx->stream;
             ctx->stream = ctx->aux_stream;
-            rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, r, 1);
+            rc = launch_gemm_tma_nt(ctx, r);
+            if (rc == 1) rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, r, 1);
             ctx->stream = main_stream;
             if (rc) return rc;
             BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_done[0], ctx->aux_stream));

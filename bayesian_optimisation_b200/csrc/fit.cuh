@@ -19,6 +19,9 @@ size_t trtri_scratch_doubles(int64_t n);
 int trtri_recursive(bogp_ctx* ctx, const double* d_l, int64_t ldl, int64_t strideL, double* d_w, int64_t ldw,
                     int64_t strideW, double* d_t, int64_t strideT, int64_t n, int batch, int64_t b_start);
 size_t packed_w_doubles(int64_t n_pad);
+struct GemmArgs;
+// TMA-fed NT GEMM (gemm_tma.cu); returns 1 when not applicable (caller falls back to the cp.async kernel)
+int launch_gemm_tma_nt(bogp_ctx* ctx, const GemmArgs& g);
 
 // one chunk of the acquisition sweep, as handed to either tensor path
 struct AcqChunk {

@@ -1,0 +1,165 @@
+// C (+)= alpha * A * B^T on the FP64 tensor path with TMA-fed operands (the Cholesky trailing update).
+//
+// The generic cp.async GEMM (gemm_f64.cuh) keeps the DMMA pipe only ~57 % busy: every thread spends
+// issue slots on address arithmetic and the CTA meets at a barrier per k step.  Here the two row-major,
+// K-contiguous operands are fetched by the TMA unit instead: a tensor map with a box of {4 k, 128 rows}
+// lands in shared memory as [row][4 doubles], which is exactly the DMMA.8x8x4 fragment order (a warp's
+// fragment = one contiguous 256-byte line, no padding, no bank conflicts).  One producer lane issues
+// 16 boxes per 32-wide k stage; 8 consumer warps (4 x 2, warp tile 32 x 64) do nothing but LDS + DMMA;
+// stages are handed over with mbarriers (no CTA-wide barrier in the main loop).
+#include "common.cuh"
+#include "gemm_f64.cuh"
+#include <cuda.h>
+
+namespace bogp {
+
+constexpr int TBM = 128, TBN = 128, TKB = 32, TSTAGES = 3;
+constexpr int kTOperandBytes = TBM * TKB * 8;                 // 32 KB
+constexpr int kTStageBytes = 2 * kTOperandBytes;              // 64 KB
+constexpr size_t kTSmem = (size_t)TSTAGES * kTStageBytes + 2 * TSTAGES * 8 + 64;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+struct TmaGemmArgs {
+    double* C; int64_t ldc;
+    int M, N, K;
+    double alpha; int accumulate, lower_only;
+};
+
+__global__ void __launch_bounds__(288, 1)
+gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaGemmArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TSTAGES * kTStageBytes);
+    uint64_t* empt = full + TSTAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+    if (g.lower_only && n0 > m0 + TBM - 1) return;
+    const int nk = (g.K + TKB - 1) / TKB;
+
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 8); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % TSTAGES;
+                if (kt >= TSTAGES) mbar_wait(&empt[s], ((kt / TSTAGES) - 1) & 1);
+                unsigned char* dst = smem_raw + (size_t)s * kTStageBytes;
+                mbar_expect_tx(&full[s], kTStageBytes);
+#pragma unroll
+                for (int kk = 0; kk < TKB / 4; kk++) {
+                    tma_load_2d(dst + kk * (TBM * 32), &mapA, kt * TKB + kk * 4, m0, &full[s]);
+                    tma_load_2d(dst + kTOperandBytes + kk * (TBN * 32), &mapB, kt * TKB + kk * 4, n0, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < nk; kt++) {
+        const int s = kt % TSTAGES;
+        mbar_wait(&full[s], (kt / TSTAGES) & 1);
+        const double* a = reinterpret_cast<const double*>(smem_raw + (size_t)s * kTStageBytes);
+        const double* b = a + TBM * TKB;
+#pragma unroll
+        for (int kk = 0; kk < TKB / 4; kk++) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) af[i] = a[(kk * TBM + wm * 32 + i * 8) * 4 + lane];     // [(row)*4 + k], lane = (row%8)*4 + k
+#pragma unroll
+            for (int j = 0; j < 8; j++) bf[j] = b[(kk * TBN + wn * 64 + j * 8) * 4 + lane];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empt[s]);
+    }
+
+    const int lr = lane >> 2, lk = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = m0 + wm * 32 + i * 8 + lr;
+        if (row >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int col = n0 + wn * 64 + j * 8 + 2 * lk;
+            if (col >= g.N) continue;
+            double* p = g.C + (int64_t)row * g.ldc + col;
+            const double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+            const bool ok0 = !g.lower_only || col <= row;
+            const bool ok1 = (col + 1 < g.N) && (!g.lower_only || col + 1 <= row);
+            if (ok0 && ok1) {
+                double2 o = make_double2(v0, v1);
+                if (g.accumulate) { const double2 c = *reinterpret_cast<double2*>(p); o.x += c.x; o.y += c.y; }
+                *reinterpret_cast<double2*>(p) = o;
+            } else {
+                if (ok0) p[0] = g.accumulate ? p[0] + v0 : v0;
+                if (ok1) p[1] = g.accumulate ? p[1] + v1 : v1;
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// rows x K row-major fp64 operand, leading dimension ld (doubles); box = {4 k, 128 rows}
+static bool make_operand_map(CUtensorMap* map, const double* base, int64_t rows, int64_t K, int64_t ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 2) != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {4, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// C (+)= alpha A B^T for one matrix (no batching).  Returns BOGP_OK, or 1 if the TMA path is not
+// applicable (caller falls back to the cp.async kernel).
+int launch_gemm_tma_nt(bogp_ctx* ctx, const GemmArgs& g) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return BOGP_OK;
+    alignas(64) CUtensorMap mapA, mapB;
+    if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb)) return 1;
+    static bool configured = false;
+    if (!configured) {
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmem));
+        configured = true;
+    }
+    TmaGemmArgs a{g.C, g.ldc, g.M, g.N, g.K, g.alpha, g.accumulate, g.lower_only};
+    dim3 grid((g.N + TBN - 1) / TBN, (g.M + TBM - 1) / TBM);
+    gemm_tma_nt_kernel<<<grid, 288, kTSmem, ctx->stream>>>(mapA, mapB, a);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
+}  // namespace bogp
