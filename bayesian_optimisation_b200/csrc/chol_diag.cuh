@@ -28,14 +28,19 @@ struct DiagArgs {
 #ifndef BOGP_DIAG_GROUPS
 #define BOGP_DIAG_GROUPS (kDiagNB / 4)
 #endif
-__global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
+struct DiagSmem {
+    double col[2][kDiagNB];    // u_i = a[i][j] before scaling (rows > j)
+    double col2[2][kDiagNB];   // u_i / a_jj
+    double xrow[2][kDiagNB];   // R[j][c]  (unscaled row j of the inverse)
+    double dg[kDiagNB];
+};
+
+// Device body: factor + invert block `kblk` of matrix `mat`; 256 threads; `sm` in shared memory.
+__device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, DiagSmem& sm) {
     constexpr int NB = kDiagNB;
-    __shared__ __align__(16) double col[2][NB];    // u_i = a[i][j] before scaling (rows > j)
-    __shared__ __align__(16) double col2[2][NB];   // u_i / a_jj
-    __shared__ __align__(16) double xrow[2][NB];   // R[j][c]  (unscaled row j of the inverse)
-    __shared__ double dg[NB];
+    double (&col)[2][NB] = sm.col; double (&col2)[2][NB] = sm.col2; double (&xrow)[2][NB] = sm.xrow; double (&dg)[NB] = sm.dg;
     const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15, lane = tid & 31;
-    double* A = g.a + blockIdx.x * g.strideA + (int64_t)g.kblk * NB * (g.lda + 1);
+    double* A = g.a + mat * g.strideA + (int64_t)g.kblk * NB * (g.lda + 1);
     const bool active = ty >= tx;
     double a[4][4], r[4][4];
 #pragma unroll
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int row = 4 * ty + i, cc = 4 * tx + c;
-            a[i][c] = (active && cc <= row) ? A[(int64_t)row * g.lda + cc] : 0.0;
+            a[i][c] = (active && cc <= row) ? __ldcg(A + (int64_t)row * g.lda + cc) : 0.0;   // L2-coherent: other CTAs may have written it
             r[i][c] = (row == cc) ? 1.0 : 0.0;
         }
     const unsigned half_mask = 0xFFFFu << (lane & 16);
@@ -105,14 +110,14 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
         const double ajj = dg[tid];
         if (!(ajj > 0.0) || isinf(ajj)) {                     // report the first bad pivot (1-based)
             const int idx = g.kblk * NB + tid + 1;
-            if (atomicCAS(g.info + blockIdx.x, 0, idx) != 0) atomicMin(g.info + blockIdx.x, idx);
+            if (atomicCAS(g.info + mat, 0, idx) != 0) atomicMin(g.info + mat, idx);
         }
         const double isd = rsqrt(ajj);
         col[0][tid] = isd;
         col2[0][tid] = ajj * isd;
     }
     __syncthreads();
-    double* W = g.w ? g.w + blockIdx.x * g.strideW + (int64_t)g.kblk * NB * (g.ldw + 1) : nullptr;
+    double* W = g.w ? g.w + mat * g.strideW + (int64_t)g.kblk * NB * (g.ldw + 1) : nullptr;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int row = 4 * ty + i;
@@ -128,11 +133,14 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
         double s = log(dg[tid]) + log(dg[tid + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) g.logdet[blockIdx.x] += s;
+        if (tid == 0) g.logdet[mat] += s;
     }
 }
 
-
+__global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
+    __shared__ __align__(16) DiagSmem sm;
+    chol_diag_block(g, (int)blockIdx.x, sm);
+}
 
 #ifdef BOGP_DIAG_BENCH
 __global__ void __launch_bounds__(256) chol_diag_kernel_v1(DiagArgs g) {

@@ -75,6 +75,7 @@ struct bogp_ctx {
     // second stream + events: the k_* panel of chunk s+1 is built while chunk s is on the tensor cores
     cudaStream_t aux_stream;
     cudaEvent_t  ev_fork, ev_panel[2], ev_done[2];
+    int64_t      inblock_launches;   // launches of the fused in-block kernel (its grid-barrier counter only grows)
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
     cudaEvent_t  ev[2];

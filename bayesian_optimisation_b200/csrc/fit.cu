@@ -162,6 +162,223 @@ static int cholesky_blocked_v1(bogp_ctx* ctx, double* d_a, int64_t n, int64_t ld
     return BOGP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// One launch for the whole serial part of a 256-column panel: factor the 256x256 diagonal block
+// (4 diagonal 64-blocks with their small panel solves and updates) and invert its factor (two
+// recursive-doubling levels).  8 CTAs share the tile work of each phase and meet at a software
+// grid barrier (global counter, release/acquire fences); all cross-CTA data is read L2-coherently
+// (cp.async.cg / ld.cg).  This replaces 26 dependent launches per panel by one.
+// ------------------------------------------------------------------------------------------------
+struct InBlockArgs {
+    double* a; int64_t lda;      // diagonal block A[ko.., ko..] lives at a + ko*(lda+1)
+    double* w; int64_t ldw;
+    double* t;                   // scratch, >= 16384 doubles
+    double* logdet; int* info;
+    unsigned* counter; unsigned base;   // grid barrier: counter value at kernel start
+    int kblk0;                   // first 64-block index of the panel (ko / 64)
+};
+constexpr int kInBlockCtas = 8;
+
+__device__ __forceinline__ void inblock_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) inblock256_kernel(InBlockArgs g) {
+    extern __shared__ __align__(16) double smem[];
+    DiagSmem& dsm = *reinterpret_cast<DiagSmem*>(smem);
+    const int cta = blockIdx.x;
+    constexpr int NB = kDiagNB;
+    double* A = g.a + (int64_t)g.kblk0 * NB * (g.lda + 1);     // 256 x 256 diagonal block
+    double* W = g.w + (int64_t)g.kblk0 * NB * (g.ldw + 1);
+    unsigned target = g.base;
+    auto barrier = [&]() { target += kInBlockCtas; inblock_barrier(g.counter, target); };
+    auto tile = [&](auto fn) { __syncthreads(); fn(); };          // shared memory is reused between tiles
+
+    for (int k = 0; k < 4; k++) {
+        if (cta == 0) {
+            DiagArgs dg{g.a, g.lda, 0, g.w, g.ldw, 0, g.logdet, g.info, g.kblk0 + k};
+            __syncthreads();
+            chol_diag_block(dg, 0, dsm);
+        }
+        if (k == 3) break;
+        barrier();
+        // panel solve: P_i = A_ik * Dinv_k^T, i = k+1..3   (in place; one CTA owns the tile)
+        if (cta < 3 - k) {
+            const int i = k + 1 + cta;
+            GemmArgs t{};
+            t.lda = g.lda; t.ldb = g.ldw; t.ldc = g.lda; t.M = NB; t.N = NB; t.K = NB; t.alpha = 1.0;
+            double* Aik = A + (int64_t)i * NB * g.lda + k * NB;
+            tile([&] { gemm_tile<64, 64, A_MK, B_NK, K_ALL>(t, Aik, W + (int64_t)k * NB * (g.ldw + 1), Aik, 0, 0, smem); });
+        }
+        barrier();
+        // update: A_ij -= P_i P_j^T, k < j <= i <= 3
+        {
+            int idx = 0;
+            for (int i = k + 1; i < 4; i++)
+                for (int j = k + 1; j <= i; j++, idx++) {
+                    if (idx % kInBlockCtas != cta) continue;
+                    GemmArgs s{};
+                    s.lda = g.lda; s.ldb = g.lda; s.ldc = g.lda; s.M = NB; s.N = NB; s.K = NB; s.alpha = -1.0; s.accumulate = 1;
+                    s.lower_only = (i == j) ? 1 : 0;
+                    tile([&] { gemm_tile<64, 64, A_MK, B_NK, K_ALL>(s, A + (int64_t)i * NB * g.lda + k * NB, A + (int64_t)j * NB * g.lda + k * NB,
+                                                                     A + (int64_t)i * NB * g.lda + j * NB, 0, 0, smem); });
+                }
+        }
+        barrier();
+    }
+    barrier();
+    // inverse, level 64: pairs (0,1), (2,3):  W21 = -W22 * (L21 * W11)
+    if (cta < 2) {
+        const int o = 2 * cta * NB;
+        double* T = g.t + cta * NB * NB;
+        GemmArgs g1{};
+        g1.lda = g.lda; g1.ldb = g.ldw; g1.ldc = NB; g1.M = NB; g1.N = NB; g1.K = NB; g1.alpha = 1.0;
+        tile([&] { gemm_tile<64, 64, A_MK, B_KN, K_GE_N>(g1, A + (int64_t)(o + NB) * g.lda + o, W + (int64_t)o * (g.ldw + 1), T, 0, 0, smem); });
+        __threadfence();
+        GemmArgs g2{};
+        g2.lda = g.ldw; g2.ldb = NB; g2.ldc = g.ldw; g2.M = NB; g2.N = NB; g2.K = NB; g2.alpha = -1.0;
+        tile([&] { gemm_tile<64, 64, A_MK, B_KN, K_LE_M>(g2, W + (int64_t)(o + NB) * (g.ldw + 1), T, W + (int64_t)(o + NB) * g.ldw + o, 0, 0, smem); });
+    }
+    barrier();
+    // level 128: T = L21 * W11 (128 x 128), then W21 = -W22 * T; 4 tiles each
+    double* T2 = g.t + 2 * NB * NB;
+    if (cta < 4) {
+        GemmArgs g1{};
+        g1.lda = g.lda; g1.ldb = g.ldw; g1.ldc = 2 * NB; g1.M = 2 * NB; g1.N = 2 * NB; g1.K = 2 * NB; g1.alpha = 1.0;
+        tile([&] { gemm_tile<64, 64, A_MK, B_KN, K_GE_N>(g1, A + (int64_t)(2 * NB) * g.lda, W, T2, (cta >> 1) * 64, (cta & 1) * 64, smem); });
+    }
+    barrier();
+    if (cta < 4) {
+        GemmArgs g2{};
+        g2.lda = g.ldw; g2.ldb = 2 * NB; g2.ldc = g.ldw; g2.M = 2 * NB; g2.N = 2 * NB; g2.K = 2 * NB; g2.alpha = -1.0;
+        tile([&] { gemm_tile<64, 64, A_MK, B_KN, K_LE_M>(g2, W + (int64_t)(2 * NB) * (g.ldw + 1), T2, W + (int64_t)(2 * NB) * g.ldw, (cta >> 1) * 64, (cta & 1) * 64, smem); });
+    }
+}
+
+// Pipelined variant of the driver below for a single matrix: the serial chain
+//   [factor + invert diagonal block] -> [panel rows of the NEXT diagonal block] -> [update that block]
+// runs on the high-priority second stream (small kernels, a few CTAs each), while everything bulky --
+// the rest of the tall panel and the trailing SYRK -- runs on the caller's stream, one panel behind.
+// Four events carry the dependencies.  All accumulation orders are the same as in the sequential
+// driver, so the factor is bit-identical.
+static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, double* d_w, int64_t ldw, double* d_logdet,
+                              int* d_info, double* d_t) {
+    constexpr int kOuter = 256;
+    cudaStream_t bs = ctx->stream, cs = ctx->aux_stream;
+    cudaEvent_t e_in = ctx->ev_panel[0], e_t1 = ctx->ev_panel[1], e_dn2 = ctx->ev_done[0], e_rest = ctx->ev_done[1];
+    struct StreamSwap { bogp_ctx* c; cudaStream_t saved; StreamSwap(bogp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; } ~StreamSwap() { c->stream = saved; } };
+    BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, bs));
+    BOGP_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
+    int rc = BOGP_OK;
+    constexpr int kInBlockPhases = 12;                         // barriers per inblock256_kernel launch
+    constexpr size_t kInBlockSmem = GemmSmem<64, 64>::bytes > sizeof(DiagSmem) ? GemmSmem<64, 64>::bytes : sizeof(DiagSmem);
+    static const bool fused = !(getenv("BOGP_FIT_FUSED") && getenv("BOGP_FIT_FUSED")[0] == '0');
+    unsigned* counter = reinterpret_cast<unsigned*>(ctx->d_flags + 16);
+    {
+        static bool configured = false;
+        if (!configured) {
+            BOGP_CUDA_CHECK(cudaFuncSetAttribute(inblock256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInBlockSmem));
+            configured = true;
+        }
+        // the barrier counter only grows; restart it long before it can wrap
+        if (ctx->inblock_launches > 30000000) { BOGP_CUDA_CHECK(cudaMemsetAsync(counter, 0, 4, cs)); ctx->inblock_launches = 0; }
+    }
+    for (int64_t ko = 0; ko < n; ko += kOuter) {
+        const int64_t w = (n - ko < kOuter) ? (n - ko) : kOuter;
+        double* Add = d_a + ko * (lda + 1);
+        double* Wdd = d_w + ko * (ldw + 1);
+        if (w == kOuter && fused) {   // ---- chain: factor and invert the diagonal block, one launch
+            InBlockArgs ia{d_a, lda, d_w, ldw, d_t, d_logdet, d_info, counter, (unsigned)(ctx->inblock_launches * kInBlockPhases * kInBlockCtas), (int)(ko / kDiagNB)};
+            ctx->inblock_launches++;
+            inblock256_kernel<<<kInBlockCtas, 256, kInBlockSmem, cs>>>(ia);
+            BOGP_LAUNCH_CHECK(ctx);
+        } else {
+            StreamSwap sw(ctx, cs);
+            for (int64_t ki = 0; ki < w; ki += kDiagNB) {
+                const int64_t k = ko + ki;
+                DiagArgs dg{d_a, lda, 0, d_w, ldw, 0, d_logdet, d_info, (int)(k / kDiagNB)};
+                chol_diag_kernel<<<1, 256, 0, cs>>>(dg);
+                BOGP_LAUNCH_CHECK(ctx);
+                const int below = (int)(w - (ki + kDiagNB));
+                if (below <= 0) break;
+                double* panel = d_a + (k + kDiagNB) * lda + k;
+                GemmArgs t{};
+                t.A = panel; t.lda = lda; t.B = d_w + k * (ldw + 1); t.ldb = ldw; t.C = panel; t.ldc = lda;
+                t.M = below; t.N = kDiagNB; t.K = kDiagNB; t.alpha = 1.0;
+                if ((rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, t, 1))) return rc;
+                GemmArgs s{};
+                s.A = panel; s.lda = lda; s.B = panel; s.ldb = lda; s.C = d_a + (k + kDiagNB) * (lda + 1); s.ldc = lda;
+                s.M = below; s.N = below; s.K = kDiagNB; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
+                if ((rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, s, 1))) return rc;
+            }
+            if ((rc = trtri_recursive(ctx, Add, lda, 0, Wdd, ldw, 0, d_t, 0, w, 1, kDiagNB))) return rc;
+        }
+        BOGP_CUDA_CHECK(cudaEventRecord(e_in, cs));
+        const int64_t row1 = ko + w;
+        const int64_t below = n - row1;
+        if (below <= 0) break;
+        const int64_t r1 = (below < kOuter) ? below : kOuter;      // rows of the next diagonal block
+        const int64_t r2 = below - r1;                              // everything under it
+        double* P1 = d_a + row1 * lda + ko;                         // panel rows of the next diagonal block
+        double* P2 = d_a + (row1 + r1) * lda + ko;
+        double* Tp = d_t + 65536;                                  // P1 staging (r1 x w, leading dimension w), past the in-block scratch
+        {   // ---- chain: panel rows R1 (out of place, small tiles), then the next diagonal block
+            StreamSwap sw(ctx, cs);
+            if (ko > 0) BOGP_CUDA_CHECK(cudaStreamWaitEvent(cs, e_dn2, 0));     // A[R1, panel] got its last update, and Tp is free again
+            GemmArgs t{};
+            t.A = P1; t.lda = lda; t.B = Wdd; t.ldb = ldw; t.C = Tp; t.ldc = w;
+            t.M = (int)r1; t.N = (int)w; t.K = (int)w; t.alpha = 1.0;
+            if ((rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, t, 1))) return rc;
+            BOGP_CUDA_CHECK(cudaEventRecord(e_t1, cs));
+            if (ko > 0) BOGP_CUDA_CHECK(cudaStreamWaitEvent(cs, e_rest, 0));    // A[R1, R1] received the previous panel's bulk update
+            GemmArgs s{};
+            s.A = Tp; s.lda = w; s.B = Tp; s.ldb = w; s.C = d_a + row1 * (lda + 1); s.ldc = lda;
+            s.M = (int)r1; s.N = (int)r1; s.K = (int)w; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
+            if ((rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, s, 1))) return rc;
+        }
+        {   // ---- bulk, on the caller's stream
+            BOGP_CUDA_CHECK(cudaStreamWaitEvent(bs, e_t1, 0));
+            // P1 belongs to L: copy it into place (off the critical path)
+            BOGP_CUDA_CHECK(cudaMemcpy2DAsync(P1, lda * sizeof(double), Tp, w * sizeof(double), w * sizeof(double), r1, cudaMemcpyDeviceToDevice, bs));
+            if (r2 > 0) {
+                BOGP_CUDA_CHECK(cudaStreamWaitEvent(bs, e_in, 0));
+                GemmArgs t{};
+                t.A = P2; t.lda = lda; t.B = Wdd; t.ldb = ldw; t.C = P2; t.ldc = lda;
+                t.M = (int)r2; t.N = (int)w; t.K = (int)w; t.alpha = 1.0;
+                if ((rc = launch_gemm<64, 256, A_MK, B_NK, K_ALL>(ctx, t, 1))) return rc;
+                GemmArgs d{};       // A[R2, R1 columns] -= P2 P1^T
+                d.A = P2; d.lda = lda; d.B = P1; d.ldb = lda; d.C = d_a + (row1 + r1) * lda + row1; d.ldc = lda;
+                d.M = (int)r2; d.N = (int)r1; d.K = (int)w; d.alpha = -1.0; d.accumulate = 1;
+                rc = launch_gemm_tma_nt(ctx, d);
+                if (rc == 1) rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, d, 1);
+                if (rc) return rc;
+            }
+            BOGP_CUDA_CHECK(cudaEventRecord(e_dn2, bs));
+            if (r2 > 0) {
+                GemmArgs r{};       // A[R2, R2] -= P2 P2^T (lower)
+                r.A = P2; r.lda = lda; r.B = P2; r.ldb = lda; r.C = d_a + (row1 + r1) * (lda + 1); r.ldc = lda;
+                r.M = (int)r2; r.N = (int)r2; r.K = (int)w; r.alpha = -1.0; r.accumulate = 1; r.lower_only = 1;
+                rc = launch_gemm_tma_nt(ctx, r);
+                if (rc == 1) rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, r, 1);
+                if (rc) return rc;
+            }
+            BOGP_CUDA_CHECK(cudaEventRecord(e_rest, bs));
+        }
+    }
+    // the caller's stream also holds the last copy of P1: nothing else to join there
+    BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, cs));            // join: the caller's stream continues after the chain
+    BOGP_CUDA_CHECK(cudaStreamWaitEvent(bs, ctx->ev_fork, 0));
+    return BOGP_OK;
+}
+
 // Blocked Cholesky with explicit inverses of the 256x256 diagonal blocks.
 // Per outer panel of 256 columns:
 //   (a) the 256x256 diagonal block is factored (NB = 64 steps inside the block only),
@@ -183,6 +400,11 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
         }
     }
     if (n % kDiagNB != 0) { set_error("cholesky: n=%lld is not a multiple of %d", (long long)n, kDiagNB); return BOGP_ERR_BAD_ARG; }
+    {
+        static const bool pipeline = !(getenv("BOGP_FIT_PIPELINE") && getenv("BOGP_FIT_PIPELINE")[0] == '0');
+        if (pipeline && batch == 1 && !ctx->profile && !getenv("BOGP_TRACE_FIT"))
+            return cholesky_pipelined(ctx, d_a, n, lda, d_w, ldw, d_logdet, d_info, d_t);
+    }
     constexpr int kOuter = 256;
     // optional phase trace (BOGP_TRACE_FIT=1): events on the main stream, read back after the loop
     static const bool trace = getenv("BOGP_TRACE_FIT") != nullptr;

@@ -42,10 +42,10 @@ struct GemmSmem {
     static constexpr size_t bytes = size_t(kStages) * kStageBytes;
 };
 
-// 256 threads = 8 warps arranged 4 (m) x 2 (n); warp tile (BM/4) x (BN/2).
+// One BM x BN output tile at (m0, n0) by the 256 threads of a CTA (8 warps arranged 4 (m) x 2 (n); warp
+// tile (BM/4) x (BN/2)).  Callable from the plain GEMM kernel below and from fused multi-phase kernels.
 template <int BM, int BN, int AL, int BL, int KR>
-__global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
-    extern __shared__ __align__(16) double smem[];
+__device__ __forceinline__ void gemm_tile(const GemmArgs& g, const double* A, const double* B, double* C, int m0, int n0, double* smem) {
     using S = GemmSmem<BM, BN>;
     double* sA = smem;
     constexpr int GSTAGES = S::kStages;
@@ -55,23 +55,7 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
     const int wm = warp >> 1, wn = warp & 1;
     constexpr int WM = BM / 4, WN = BN / 2, MI = WM / 8, NI = WN / 8;
 
-    // Tiles with a restricted k range are scheduled heaviest-first: K_LE_M grows with m (row blocks in
-    // reverse order), K_GE_N shrinks with n (the column block becomes the slow grid index, ascending).
-    int bx = (int)blockIdx.x, by = (int)blockIdx.y;
-    if (KR == K_LE_M) by = (int)(gridDim.y - 1 - blockIdx.y);
-    if (KR == K_GE_N) {
-        const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x);
-        by = lin % (int)gridDim.y;
-        bx = lin / (int)gridDim.y;
-    }
-    const int m0 = by * BM, n0 = bx * BN;
     if (g.lower_only && n0 > m0 + BM - 1) return;
-
-    const int zi = g.inner > 1 ? (int)(blockIdx.z % g.inner) : (g.inner == 1 ? 0 : (int)blockIdx.z);
-    const int zo = g.inner >= 1 ? (int)(blockIdx.z / g.inner) : 0;
-    const double* A = g.A + zi * g.strideA + zo * g.strideA2;
-    const double* B = g.B + zi * g.strideB + zo * g.strideB2;
-    double*       C = g.C + zi * g.strideC + zo * g.strideC2;
 
     int kbeg = 0, kend = g.K;
     if (KR == K_GE_N) kbeg = (n0 / GK) * GK;
@@ -174,14 +158,32 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
             const bool ok1 = (col + 1 < g.N) && (!g.lower_only || col + 1 <= row);
             if (ok0 && ok1) {
                 double2 o = make_double2(v0, v1);
-                if (g.accumulate) { double2 c = *reinterpret_cast<double2*>(p); o.x += c.x; o.y += c.y; }
+                if (g.accumulate) { double2 c = __ldcg(reinterpret_cast<const double2*>(p)); o.x += c.x; o.y += c.y; }   // L2-coherent read
                 *reinterpret_cast<double2*>(p) = o;
             } else {
-                if (ok0) p[0] = g.accumulate ? p[0] + v0 : v0;
-                if (ok1) p[1] = g.accumulate ? p[1] + v1 : v1;
+                if (ok0) p[0] = g.accumulate ? __ldcg(p) + v0 : v0;
+                if (ok1) p[1] = g.accumulate ? __ldcg(p + 1) + v1 : v1;
             }
         }
     }
+}
+
+template <int BM, int BN, int AL, int BL, int KR>
+__global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double smem[];
+    // Tiles with a restricted k range are scheduled heaviest-first: K_LE_M grows with m (row blocks in
+    // reverse order), K_GE_N shrinks with n (the column block becomes the slow grid index, ascending).
+    int bx = (int)blockIdx.x, by = (int)blockIdx.y;
+    if (KR == K_LE_M) by = (int)(gridDim.y - 1 - blockIdx.y);
+    if (KR == K_GE_N) {
+        const int lin = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+        by = lin % (int)gridDim.y;
+        bx = lin / (int)gridDim.y;
+    }
+    const int zi = g.inner > 1 ? (int)(blockIdx.z % g.inner) : (g.inner == 1 ? 0 : (int)blockIdx.z);
+    const int zo = g.inner >= 1 ? (int)(blockIdx.z / g.inner) : 0;
+    gemm_tile<BM, BN, AL, BL, KR>(g, g.A + zi * g.strideA + zo * g.strideA2, g.B + zi * g.strideB + zo * g.strideB2,
+                                  g.C + zi * g.strideC + zo * g.strideC2, by * BM, bx * BN, smem);
 }
 
 template <int BM, int BN, int AL, int BL, int KR>
