@@ -510,6 +510,14 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
 // as two batched GEMMs that skip the structurally-zero k range.
 // `d_t` needs trtri_scratch_doubles(n) doubles per matrix.
 // ------------------------------------------------------------------------------------------------
+// Scratch of cholesky_blocked + trtri_recursive per matrix: the recursion's T blocks, the fused in-block
+// kernel's T blocks (2*64^2 + 128^2) and, past offset 65536, the staged panel rows P1 (256 x 256).
+size_t cholesky_scratch_doubles(int64_t n) {
+    const size_t t = trtri_scratch_doubles(n);
+    const size_t c = n > 256 ? 131072 : 24576;
+    return t > c ? t : c;
+}
+
 size_t trtri_scratch_doubles(int64_t n) {
     size_t need = 0;
     for (int64_t b = kDiagNB; b < n; b *= 2) {
@@ -690,7 +698,7 @@ static FitLayout fit_layout(int64_t n, int dim) {
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     l.x = take(np * dim * 8); l.y = take(np * 8); l.ell = take(BOGP_MAX_DIM * 8);
     l.a = take((size_t)np * np * 8); l.w = take((size_t)np * np * 8);
-    size_t shared = packed_w_doubles(np); size_t tneed = trtri_scratch_doubles(np);
+    size_t shared = packed_w_doubles(np); size_t tneed = cholesky_scratch_doubles(np);
     // the trtri scratch and the packed W are never live at the same time -> but keep them
     // separate when the scratch is the larger one (ragged block counts)
     l.wp = take((shared > tneed ? shared : tneed) * 8);

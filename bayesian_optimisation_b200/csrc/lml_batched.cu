@@ -234,7 +234,7 @@ static LmlLayout lml_layout(int64_t n, int dim, int64_t R, int want_grad) {
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
     if (n <= 64) { l.info = take(R * 4); l.total = off; l.n_pad = n; return l; }
     const int64_t np = (n + kDiagNB - 1) / kDiagNB * kDiagNB; l.n_pad = np;
-    l.tper = trtri_scratch_doubles(np);
+    l.tper = cholesky_scratch_doubles(np);
     l.x = take(np * dim * 8); l.y = take(np * 8); l.il = take(R * dim * 8);
     l.a = take((size_t)R * np * np * 8); l.w = take((size_t)R * np * np * 8); l.t = take((size_t)R * l.tper * 8);
     l.alpha = take(R * np * 8); l.v = take(R * np * 8); l.logdet = take(R * 8); l.info = take(R * 4);

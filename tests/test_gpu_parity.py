@@ -255,7 +255,7 @@ def test_nlml_batched_small_matches_literal_reference_formula(eng, n, d):
         np.testing.assert_allclose(grad[r], gref, rtol=1e-6, atol=1e-6 * np.abs(gref).max())
 
 
-@pytest.mark.parametrize("n,d,R", [(100, 3, 5), (512, 8, 6), (130, 2, 3)])
+@pytest.mark.parametrize("n,d,R", [(100, 3, 5), (512, 8, 6), (130, 2, 3), (300, 4, 1), (256, 3, 1), (200, 3, 1), (700, 5, 1)])
 def test_nlml_batched_large_matches_oracle(eng, n, d, R):
     rng = np.random.default_rng(n + R)
     X, y, _ = o.synthetic_problem(n, d, seed=n)
