@@ -487,3 +487,55 @@ def test_fit_enqueue_is_graph_capturable(eng):
     _lib.check(eng.lib.bogp_fit_status(hg, C.byref(replay)))
     eng.lib.bogp_fit_destroy(hg)
     assert replay.value == eager.value
+
+
+# ------------------------------------------------------------------ workspace bounds (compute-sanitizer is closed on this pool)
+@pytest.mark.parametrize("n,d", [(1, 1), (64, 2), (200, 3), (256, 4), (257, 3), (300, 4), (512, 5), (600, 6), (1100, 3)])
+def test_kernels_stay_inside_their_declared_workspaces(eng, n, d):
+    """Every entry point gets a workspace of exactly the size it asks for, followed by a guard region
+    filled with a pattern; the guard must be intact afterwards."""
+    import ctypes as C
+    import torch
+    from bayesian_optimisation_b200 import _lib
+    from bayesian_optimisation_b200.engine import Candidates
+    e = _consts()
+    GUARD = 1 << 16
+    X, y, ell = o.synthetic_problem(n, d, seed=n)
+    dX, dy, dl = eng.to_device(X), eng.to_device(y), eng.to_device(ell)
+    eng._sync_stream()
+
+    def guarded(nbytes):
+        nbytes = (nbytes + 255) // 256 * 256
+        buf = torch.full((nbytes + GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, nbytes
+
+    def intact(buf, nbytes):
+        torch.cuda.synchronize()
+        return bool((buf[nbytes:] == 0xA5).all().item())
+
+    # fit
+    ws, nb = guarded(eng.lib.bogp_fit_workspace_bytes(n, d))
+    h, nl = C.c_void_p(), C.c_double()
+    _lib.check(eng.lib.bogp_fit_create(eng._ctx, dX.data_ptr(), dy.data_ptr(), n, d, dl.data_ptr(), e.JITTER_POSTERIOR,
+                                       ws.data_ptr(), nb, C.byref(h), C.byref(nl)))
+    assert intact(ws, nb), "fit wrote past its workspace"
+    ref = o.nlml(X, y, ell) if n > 1 else None
+    # acquire (both buffer sets of the two-stream path)
+    P = eng.to_device(np.random.default_rng(1).random((700, d)))
+    cd = Candidates(); cd.d_points, cd.d_axes, cd.h_axis_len, cd.c_total, cd.cross_jitter = P.data_ptr(), None, None, 700, 0.0
+    aws, anb = guarded(eng.lib.bogp_acquire_workspace_bytes(h, 512))
+    bs, bi = C.c_double(), C.c_int64()
+    _lib.check(eng.lib.bogp_acquire(eng._ctx, h, C.byref(cd), 0, 700, 0, 4.0, 0.0, e.PRIOR_DIAG, None, None, None,
+                                    aws.data_ptr(), anb, C.byref(bs), C.byref(bi)))
+    assert intact(aws, anb), "acquire wrote past its workspace"
+    eng.lib.bogp_fit_destroy(h)
+    # batched LML, single and several restarts, with gradient
+    for R in (1, 3):
+        ells = eng.to_device(np.tile(ell, (R, 1)) * (1 + 0.1 * np.arange(R))[:, None])
+        out = torch.empty(R, dtype=torch.float64, device="cuda"); grad = torch.empty((R, d), dtype=torch.float64, device="cuda")
+        lws, lnb = guarded(max(256, eng.lib.bogp_nlml_batched_workspace_bytes(n, d, R, 1)))
+        _lib.check(eng.lib.bogp_nlml_batched(eng._ctx, dX.data_ptr(), dy.data_ptr(), n, d, ells.data_ptr(), R, e.JITTER_LML,
+                                             out.data_ptr(), grad.data_ptr(), lws.data_ptr(), lnb))
+        assert intact(lws, lnb), f"nlml_batched (R={R}) wrote past its workspace"
+        if ref is not None:
+            assert abs(out[0].item() - ref) <= RTOL * abs(ref)
