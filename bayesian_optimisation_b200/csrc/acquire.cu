@@ -367,10 +367,9 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
     char* base = static_cast<char*>(d_workspace);
     double* panel = (double*)(base + l.panel); double* qpart = (double*)(base + l.qpart); double* mupart = (double*)(base + l.mupart);
 
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need(ctx->device)) {
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmem));
-        configured = true;
     }
     cudaStream_t st = ctx->stream;
     double* best = ctx->d_scalars; long long* besti = reinterpret_cast<long long*>(ctx->d_scalars + 1);

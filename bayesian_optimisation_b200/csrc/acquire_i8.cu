@@ -439,10 +439,9 @@ int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
 }
 
 int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need(ctx->device)) {
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kI8Smem));
-        configured = true;
     }
     const int nct = (int)((a.cur + kI8BN - 1) / kI8BN);
     const bool ub = a.n_pad <= 8192;

@@ -23,6 +23,12 @@ constexpr int kAcqStages = 5;
 
 void set_error(const char* fmt, ...);
 
+// Function attributes (opt-in shared memory) are per device: `flags` is a per-kernel static array.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool need(int device) { if (device < 0 || device >= 64) return true; if (done[device]) return false; done[device] = true; return true; }
+};
+
 #define BOGP_CUDA_CHECK(expr)                                                             \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

@@ -283,10 +283,9 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
     static const bool fused = !(getenv("BOGP_FIT_FUSED") && getenv("BOGP_FIT_FUSED")[0] == '0');
     unsigned* counter = reinterpret_cast<unsigned*>(ctx->d_flags + 16);
     {
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce configured;
+        if (configured.need(ctx->device)) {
             BOGP_CUDA_CHECK(cudaFuncSetAttribute(inblock256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInBlockSmem));
-            configured = true;
         }
         // the barrier counter only grows; restart it long before it can wrap
         if (ctx->inblock_launches > 30000000) { BOGP_CUDA_CHECK(cudaMemsetAsync(counter, 0, 4, cs)); ctx->inblock_launches = 0; }
@@ -393,10 +392,9 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
                      int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT) {
     if (!d_t) return cholesky_blocked_v1(ctx, d_a, n, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, batch);
     {   // same shared-memory carve-out as the GEMMs around it: no SM reconfiguration between the kernels of the chain
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce configured;
+        if (configured.need(ctx->device)) {
             BOGP_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            configured = true;
         }
     }
     if (n % kDiagNB != 0) { set_error("cholesky: n=%lld is not a multiple of %d", (long long)n, kDiagNB); return BOGP_ERR_BAD_ARG; }

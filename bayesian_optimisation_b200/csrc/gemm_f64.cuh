@@ -189,12 +189,11 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g) {
 template <int BM, int BN, int AL, int BL, int KR>
 inline int launch_gemm(bogp_ctx* ctx, const GemmArgs& g, int batch) {
     auto kern = gemm_f64_kernel<BM, BN, AL, BL, KR>;
-    static bool configured = false;
+    static DeviceOnce configured;
     constexpr size_t smem = GemmSmem<BM, BN>::bytes;
-    if (!configured) {
+    if (configured.need(ctx->device)) {
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
     }
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return BOGP_OK;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);

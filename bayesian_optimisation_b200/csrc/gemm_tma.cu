@@ -150,10 +150,9 @@ int launch_gemm_tma_nt(bogp_ctx* ctx, const GemmArgs& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return BOGP_OK;
     alignas(64) CUtensorMap mapA, mapB;
     if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb)) return 1;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need(ctx->device)) {
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmem));
-        configured = true;
     }
     TmaGemmArgs a{g.C, g.ldc, g.M, g.N, g.K, g.alpha, g.accumulate, g.lower_only};
     dim3 grid((g.N + TBN - 1) / TBN, (g.M + TBM - 1) / TBM);

@@ -265,10 +265,9 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
     int* info = (int*)(base + l.info);
     BOGP_CUDA_CHECK(cudaMemsetAsync(info, 0, r * 4, st));
     if (n <= 64) {
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce configured;
+        if (configured.need(ctx->device)) {
             BOGP_CUDA_CHECK(cudaFuncSetAttribute(nlml_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
-            configured = true;
         }
         SmallArgs a{d_x, d_y, d_ell, d_nlml_out, d_grad_out, info, (int)n, dim, jitter};
         nlml_small_kernel<<<(unsigned)r, 256, kSmallSmem, st>>>(a);
