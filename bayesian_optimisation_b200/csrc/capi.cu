@@ -53,6 +53,8 @@ extern "C" int bogp_create(int device, bogp_ctx** out) {
         BOGP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         BOGP_CUDA_CHECK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
     }
+    BOGP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux2_stream, cudaStreamNonBlocking));
+    BOGP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_aux2, cudaEventDisableTiming));
     BOGP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         BOGP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_panel[i], cudaEventDisableTiming));
@@ -90,7 +92,9 @@ extern "C" void bogp_destroy(bogp_ctx* ctx) {
     cudaEventDestroy(ctx->ev[0]); cudaEventDestroy(ctx->ev[1]);
     cudaEventDestroy(ctx->ev_fork);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_panel[i]); cudaEventDestroy(ctx->ev_done[i]); }
+    cudaEventDestroy(ctx->ev_aux2);
     cudaStreamDestroy(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux2_stream);
     cudaFree(ctx->d_scalars); cudaFree(ctx->d_flags); cudaFree(ctx->d_block_score); cudaFree(ctx->d_block_index);
     delete ctx;
 }

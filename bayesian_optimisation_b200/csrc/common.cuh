@@ -79,8 +79,9 @@ struct bogp_ctx {
     double*      h_pinned;      // 64 doubles pinned host staging
     // optional per-kernel timing of the acquisition sweep (bogp_profile): CUDA events on the launching stream
     // second stream + events: the k_* panel of chunk s+1 is built while chunk s is on the tensor cores
-    cudaStream_t aux_stream;
-    cudaEvent_t  ev_fork, ev_panel[2], ev_done[2];
+    cudaStream_t aux_stream;      // high priority: serial chains / panel builder
+    cudaStream_t aux2_stream;     // default priority: work that may fill idle SMs (interleaved triangular inverse)
+    cudaEvent_t  ev_fork, ev_panel[2], ev_done[2], ev_aux2;
     int64_t      inblock_launches;   // launches of the fused in-block kernel (its grid-barrier counter only grows)
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;

@@ -269,15 +269,54 @@ __global__ void __launch_bounds__(256) inblock256_kernel(InBlockArgs g) {
 // the rest of the tall panel and the trailing SYRK -- runs on the caller's stream, one panel behind.
 // Four events carry the dependencies.  All accumulation orders are the same as in the sequential
 // driver, so the factor is bit-identical.
+struct StreamSwap {
+    bogp_ctx* c; cudaStream_t saved;
+    StreamSwap(bogp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
+
 static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, double* d_w, int64_t ldw, double* d_logdet,
-                              int* d_info, double* d_t) {
+                              int* d_info, double* d_t, int64_t* w_level) {
     constexpr int kOuter = 256;
     cudaStream_t bs = ctx->stream, cs = ctx->aux_stream;
     cudaEvent_t e_in = ctx->ev_panel[0], e_t1 = ctx->ev_panel[1], e_dn2 = ctx->ev_done[0], e_rest = ctx->ev_done[1];
-    struct StreamSwap { bogp_ctx* c; cudaStream_t saved; StreamSwap(bogp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; } ~StreamSwap() { c->stream = saved; } };
     BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, bs));
     BOGP_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
     int rc = BOGP_OK;
+    // Interleaved triangular inverse (n = 256 * 2^m, n >= 1024, caller asked for it): the recursive-doubling
+    // merges W21 = -W22 (L21 W11) are issued on the bulk stream as soon as their inputs are final -- the
+    // product T = L21 W11 when the left block is complete, the second product when the right block is --
+    // so that only one GEMM per level is left after the last panel.  One T buffer per level.
+    const int64_t npan = n / kOuter;
+    const bool interleave = w_level && n >= 1024 && n % kOuter == 0 && (npan & (npan - 1)) == 0;
+    cudaStream_t ts = ctx->aux2_stream;
+    auto schedule_trtri = [&](int64_t i) -> int {          // panel i (and all bulk work of iteration i) has been enqueued
+        // third stream: the merges fill idle SMs without delaying the bulk stream (which the chain waits on)
+        BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_in, 0));      // W blocks of panel i (chain)
+        BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_dn2, 0));     // L rows below panel i are final (bulk)
+        StreamSwap sw(ctx, ts);
+        size_t toff = 131072;
+        for (int64_t b = kOuter; b < n; toff += (size_t)(b * b), b *= 2) {
+            const int64_t nb = b / kOuter;
+            if ((i + 1) % nb != 0) break;
+            const int64_t q = (i + 1) / nb - 1;                 // the size-b block that has just been completed
+            double* T = d_t + toff;
+            if (q % 2 == 0) {                                   // left block of its pair: T = L21 * W11
+                const int64_t o = q * b;
+                GemmArgs g1{};
+                g1.A = d_a + (o + b) * lda + o; g1.lda = lda; g1.B = d_w + o * (ldw + 1); g1.ldb = ldw; g1.C = T; g1.ldc = b;
+                g1.M = (int)b; g1.N = (int)b; g1.K = (int)b; g1.alpha = 1.0;
+                return launch_gemm<128, 128, A_MK, B_KN, K_GE_N>(ctx, g1, 1);
+            }
+            const int64_t o = (q - 1) * b;                      // right block: W21 = -W22 * T
+            GemmArgs g2{};
+            g2.A = d_w + (o + b) * (ldw + 1); g2.lda = ldw; g2.B = T; g2.ldb = b; g2.C = d_w + (o + b) * ldw + o; g2.ldc = ldw;
+            g2.M = (int)b; g2.N = (int)b; g2.K = (int)b; g2.alpha = -1.0;
+            int r = launch_gemm<128, 128, A_MK, B_KN, K_LE_M>(ctx, g2, 1);
+            if (r) return r;
+        }
+        return BOGP_OK;
+    };
     constexpr int kInBlockPhases = 12;                         // barriers per inblock256_kernel launch
     constexpr size_t kInBlockSmem = GemmSmem<64, 64>::bytes > sizeof(DiagSmem) ? GemmSmem<64, 64>::bytes : sizeof(DiagSmem);
     static const bool fused = !(getenv("BOGP_FIT_FUSED") && getenv("BOGP_FIT_FUSED")[0] == '0');
@@ -323,7 +362,10 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
         BOGP_CUDA_CHECK(cudaEventRecord(e_in, cs));
         const int64_t row1 = ko + w;
         const int64_t below = n - row1;
-        if (below <= 0) break;
+        if (below <= 0) {
+            if (interleave && (rc = schedule_trtri(ko / kOuter))) return rc;
+            break;
+        }
         const int64_t r1 = (below < kOuter) ? below : kOuter;      // rows of the next diagonal block
         const int64_t r2 = below - r1;                              // everything under it
         double* P1 = d_a + row1 * lda + ko;                         // panel rows of the next diagonal block
@@ -370,9 +412,14 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
                 if (rc) return rc;
             }
             BOGP_CUDA_CHECK(cudaEventRecord(e_rest, bs));
+            if (interleave && (rc = schedule_trtri(ko / kOuter))) return rc;
         }
     }
-    // the caller's stream also holds the last copy of P1: nothing else to join there
+    if (w_level) *w_level = interleave ? n : kOuter;
+    if (interleave) {
+        BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_aux2, ts));
+        BOGP_CUDA_CHECK(cudaStreamWaitEvent(bs, ctx->ev_aux2, 0));
+    }
     BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, cs));            // join: the caller's stream continues after the chain
     BOGP_CUDA_CHECK(cudaStreamWaitEvent(bs, ctx->ev_fork, 0));
     return BOGP_OK;
@@ -389,7 +436,8 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
 // absent the plain two-level driver is used.  On return the aligned 256-blocks of W hold the
 // inverses of the corresponding blocks of L (trtri_recursive continues from block size 256).
 int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
-                     int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT) {
+                     int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT, int64_t* w_level) {
+    if (w_level) *w_level = kDiagNB;
     if (!d_t) return cholesky_blocked_v1(ctx, d_a, n, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, batch);
     {   // same shared-memory carve-out as the GEMMs around it: no SM reconfiguration between the kernels of the chain
         static DeviceOnce configured;
@@ -401,7 +449,7 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
     {
         static const bool pipeline = !(getenv("BOGP_FIT_PIPELINE") && getenv("BOGP_FIT_PIPELINE")[0] == '0');
         if (pipeline && batch == 1 && !ctx->profile && !getenv("BOGP_TRACE_FIT"))
-            return cholesky_pipelined(ctx, d_a, n, lda, d_w, ldw, d_logdet, d_info, d_t);
+            return cholesky_pipelined(ctx, d_a, n, lda, d_w, ldw, d_logdet, d_info, d_t, w_level);
     }
     constexpr int kOuter = 256;
     // optional phase trace (BOGP_TRACE_FIT=1): events on the main stream, read back after the loop
@@ -494,7 +542,7 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
         cudaStreamSynchronize(ctx->stream);
         double ph[5] = {0, 0, 0, 0, 0};
         for (size_t i = 0; i + 1 < tev.size(); i++) { float ms; cudaEventElapsedTime(&ms, tev[i], tev[i + 1]); ph[i % 5] += ms; }
-        fprintf(stderr, "[bogp fit trace n=%lld] diag-block factor %.3f ms, block inverse %.3f ms, tall panel %.3f ms, next-panel update %.3f ms, (gap to next panel) %.3f ms\n",
+        (void)0; fprintf(stderr, "[bogp fit trace n=%lld] diag-block factor %.3f ms, block inverse %.3f ms, tall panel %.3f ms, next-panel update %.3f ms, (gap to next panel) %.3f ms\n",
                 (long long)n, ph[0], ph[1], ph[2], ph[3], ph[4]);
         for (auto e : tev) cudaEventDestroy(e);
     }
@@ -725,7 +773,7 @@ extern "C" int bogp_cholesky(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda,
     if (!ctx || !d_a || !d_linv || !d_logdet || !d_info || n <= 0 || lda < n) { set_error("bogp_cholesky: bad argument"); return BOGP_ERR_BAD_ARG; }
     BOGP_CUDA_CHECK(cudaMemsetAsync(d_logdet, 0, sizeof(double), ctx->stream));
     BOGP_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
-    return cholesky_blocked(ctx, d_a, n, lda, 0, d_linv, lda, 0, d_logdet, d_info, 1, nullptr, 0);
+    return cholesky_blocked(ctx, d_a, n, lda, 0, d_linv, lda, 0, d_logdet, d_info, 1, nullptr, 0, nullptr);
 }
 
 static int fit_enqueue(bogp_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int dim, const double* d_ell,
@@ -794,9 +842,9 @@ static int fit_enqueue(bogp_ctx* ctx, const double* d_x, const double* d_y, int6
     // K1 (lower tiles; identity in the padding)
     FIT_TRY(launch_gram(ctx, f->x_pad, np, n, f->x_pad, np, n, dim, f->inv_ell2, jitter, f->a, np, true, 1, 0));
     // K2
-    FIT_TRY(cholesky_blocked(ctx, f->a, np, np, 0, f->w, np, 0, f->scalars, f->info, 1, f->t, 0));
-    // W = L^-1 (the aligned 256-blocks are already inverted)
-    FIT_TRY(trtri_recursive(ctx, f->a, np, 0, f->w, np, 0, f->t, 0, np, 1, 256));
+    int64_t w_level = 0;     // block size up to which W = L^-1 is already complete
+    FIT_TRY(cholesky_blocked(ctx, f->a, np, np, 0, f->w, np, 0, f->scalars, f->info, 1, f->t, 0, &w_level));
+    if (w_level < np) FIT_TRY(trtri_recursive(ctx, f->a, np, 0, f->w, np, 0, f->t, 0, np, 1, w_level < 256 ? 256 : w_level));
     // alpha = W^T W y
     FIT_TRY(launch_alpha(ctx, f->w, np, 0, f->y_pad, f->v, f->alpha, (int)np, 1));
     nlml_finish_kernel<<<1, 256, 0, st>>>(f->y_pad, f->alpha, (int)np, (int)n, f->scalars); ctx->launches++;

@@ -14,7 +14,7 @@ int launch_alpha(bogp_ctx* ctx, const double* d_w, int64_t ldw, int64_t strideW,
                  double* d_alpha, int n, int batch);
 
 int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
-                     int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT);
+                     int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT, int64_t* w_level = nullptr);
 size_t trtri_scratch_doubles(int64_t n);
 size_t cholesky_scratch_doubles(int64_t n);
 int trtri_recursive(bogp_ctx* ctx, const double* d_l, int64_t ldl, int64_t strideL, double* d_w, int64_t ldw,
