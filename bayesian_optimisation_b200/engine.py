@@ -119,6 +119,14 @@ class GPEngine:
             return a.to(device=self.device, dtype=dtype).contiguous()
         return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
 
+    def to_host(self, t: torch.Tensor) -> np.ndarray:
+        """Device tensor -> numpy array through pinned host memory (torch's caching host allocator);
+        the array owns its buffer, which returns to the cache when the array is collected."""
+        host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
     @property
     def launches(self) -> int:
         return int(self.lib.bogp_launch_count(self._ctx))

@@ -141,8 +141,8 @@ class PointSelector():
         finally:
             fit.close()
         self._dev = (res.mu, res.sigma)
-        self.mean_func = res.mu.cpu().numpy().reshape(self.feature_domain)
-        self.cov_func = res.sigma.cpu().numpy().reshape(self.feature_domain)
+        self.mean_func = eng.to_host(res.mu).reshape(self.feature_domain)
+        self.cov_func = eng.to_host(res.sigma).reshape(self.feature_domain)
         self._dev_host = (self.mean_func, self.cov_func)
 
         self.measured_pts = self.measured_pts.tolist()
@@ -193,7 +193,7 @@ class PointSelector():
         mu, sigma = self._device_mu_sigma()
         res = self._eng().score_argmax(mu, sigma, kind=kind, explore=explore, f_best=f_best)
         shape = np.shape(self.mean_func)
-        self.acq_func_eval = res.acq.cpu().numpy().reshape(shape)
+        self.acq_func_eval = self._eng().to_host(res.acq).reshape(shape)
         return np.array(np.unravel_index(res.best_index, shape), dtype=np.int64)
 
     def lower_confidence_bound(self, explore=4):
