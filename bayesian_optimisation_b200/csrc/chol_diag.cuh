@@ -6,8 +6,10 @@ namespace bogp {
 
 // ------------------------------------------------------------------------------------------------
 // K2 diagonal block: 64x64 Cholesky + inverse of the factor, one CTA per matrix of the batch.
-// The pivot is broadcast through shared memory; the 4 partial sums of each inverse entry are
-// combined with warp shuffles.
+// Register-tiled (4x4 per thread, for the matrix and for the inverse), square-root-free inner loop,
+// columns in groups of four with one barrier per group (see chol_diag_block).  The serial chain is
+// latency-bound: a dependent fp64 op, a 64-bit shuffle and rcp.approx.f64 each cost ~24 cycles on
+// B200 (profiles/r01_latency_bench.txt).
 // ------------------------------------------------------------------------------------------------
 struct DiagArgs {
     double* a; int64_t lda; int64_t strideA;
@@ -29,6 +31,176 @@ struct DiagArgs {
 #define BOGP_DIAG_GROUPS (kDiagNB / 4)
 #endif
 struct DiagSmem {
+    double colU[2][4][kDiagNB];   // u_p[i] = A[i][j0+p] after the in-group updates (rows > j0+p, else 0)
+    double colC[2][4][kDiagNB];   // u_p[i] / a_pp
+    double rows[2][4][kDiagNB];   // R[j0+p][c] as it was when the group started
+    double mul[2][4][4];          // in-group multipliers M[p][q] = colC[q][row j0+p], q < p
+    double dg[kDiagNB];
+};
+
+__device__ __forceinline__ double rcp_newton(double x) {   // hardware seed + 2 Newton steps (~1 ulp)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+
+// Device body: factor + invert block `kblk` of matrix `mat`; 256 threads; `sm` in shared memory.
+//
+// Columns are processed in groups of 4 with ONE barrier per group:
+//   * the 16 owners of the group's columns (one half-warp) eliminate the 64 x 4 panel among themselves --
+//     pivot and the three in-group multipliers travel by warp shuffles, one hardware-seeded reciprocal
+//     per column is the only long-latency step;
+//   * after the barrier every thread applies the rank-4 update to its 4x4 registers.  For the inverse
+//     (R starts as I and becomes L^-1 up to a row scaling) the four pivot rows are published as they
+//     were when the group started; the in-group dependencies are folded into the coefficients with the
+//     4x4 unit-triangular multiplier matrix (6 FMAs per row) instead of a second barrier.
+__device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, DiagSmem& sm) {
+    constexpr int NB = kDiagNB;
+    const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15, lane = tid & 31;
+    double* A = g.a + mat * g.strideA + (int64_t)g.kblk * NB * (g.lda + 1);
+    const bool active = ty >= tx;
+    double a[4][4], r[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int row = 4 * ty + i, cc = 4 * tx + c;
+            a[i][c] = (active && cc <= row) ? __ldcg(A + (int64_t)row * g.lda + cc) : 0.0;   // L2-coherent: other CTAs may have written it
+            r[i][c] = (row == cc) ? 1.0 : 0.0;
+        }
+    const unsigned half_mask = 0xFFFFu << (lane & 16);
+    for (int jb = 0; jb < NB / 4; jb++) {
+        const int j0 = 4 * jb, buf = jb & 1;
+        if (tx == jb) {                                       // the half-warp that owns columns j0..j0+3 (all 16 lanes)
+            const int dl = (lane & 16) + jb;                  // lane of the diagonal thread (ty == jb)
+            double up[4][4], cp[4][4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const double app = __shfl_sync(half_mask, a[p][p], dl);
+                const double rinv = rcp_newton(app);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    up[p][i] = (4 * ty + i > j0 + p) ? a[i][p] : 0.0;      // rows <= j0+p are exact zeros: readers need no masks
+                    cp[p][i] = up[p][i] * rinv;
+                }
+#pragma unroll
+                for (int q = p + 1; q < 4; q++) {             // in-group update of the later columns
+                    const double s = __shfl_sync(half_mask, a[q][p], dl);   // u_p at row j0+q
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a[i][q] -= cp[p][i] * s;
+                }
+                if (ty == jb) sm.dg[j0 + p] = app;
+            }
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                *reinterpret_cast<double2*>(&sm.colU[buf][p][4 * ty])     = make_double2(up[p][0], up[p][1]);
+                *reinterpret_cast<double2*>(&sm.colU[buf][p][4 * ty + 2]) = make_double2(up[p][2], up[p][3]);
+                *reinterpret_cast<double2*>(&sm.colC[buf][p][4 * ty])     = make_double2(cp[p][0], cp[p][1]);
+                *reinterpret_cast<double2*>(&sm.colC[buf][p][4 * ty + 2]) = make_double2(cp[p][2], cp[p][3]);
+            }
+            if (ty == jb) {
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) sm.mul[buf][p][q] = (q < p) ? cp[q][p] : 0.0;
+            }
+        }
+        if (ty == jb && active) {                             // owners of rows j0..j0+3 of R (zero right of the diagonal)
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                *reinterpret_cast<double2*>(&sm.rows[buf][p][4 * tx])     = make_double2(r[p][0], r[p][1]);
+                *reinterpret_cast<double2*>(&sm.rows[buf][p][4 * tx + 2]) = make_double2(r[p][2], r[p][3]);
+            }
+        }
+        __syncthreads();
+        if (active && 4 * ty + 3 > j0) {
+            double c[4][4];                                   // c[p][i] = colC_p[row i]
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const double2 c01 = *reinterpret_cast<const double2*>(&sm.colC[buf][p][4 * ty]);
+                const double2 c23 = *reinterpret_cast<const double2*>(&sm.colC[buf][p][4 * ty + 2]);
+                c[p][0] = c01.x; c[p][1] = c01.y; c[p][2] = c23.x; c[p][3] = c23.y;
+            }
+            if (tx > jb) {                                    // trailing columns (the group's own columns were updated by their owners)
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const double2 k01 = *reinterpret_cast<const double2*>(&sm.colU[buf][p][4 * tx]);
+                    const double2 k23 = *reinterpret_cast<const double2*>(&sm.colU[buf][p][4 * tx + 2]);
+                    const double cc[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+                    for (int cidx = 0; cidx < 4; cidx++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) a[i][cidx] -= c[p][i] * cc[cidx];
+                }
+            }
+            if (tx <= jb) {                                   // inverse: fold the in-group dependencies into the coefficients
+                double m[4][4];
+#pragma unroll
+                for (int p = 1; p < 4; p++)
+#pragma unroll
+                    for (int q = 0; q < p; q++) m[p][q] = sm.mul[buf][p][q];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {                 // d = M^-T c  (M unit lower triangular)
+                    c[2][i] -= m[3][2] * c[3][i];
+                    c[1][i] -= m[2][1] * c[2][i] + m[3][1] * c[3][i];
+                    c[0][i] -= m[1][0] * c[1][i] + m[2][0] * c[2][i] + m[3][0] * c[3][i];
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const double2 x01 = *reinterpret_cast<const double2*>(&sm.rows[buf][p][4 * tx]);
+                    const double2 x23 = *reinterpret_cast<const double2*>(&sm.rows[buf][p][4 * tx + 2]);
+                    const double xr[4] = {x01.x, x01.y, x23.x, x23.y};
+#pragma unroll
+                    for (int cidx = 0; cidx < 4; cidx++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) r[i][cidx] -= c[p][i] * xr[cidx];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    double (&isd_s)[NB] = sm.colU[0][0];
+    double (&d_s)[NB] = sm.colU[0][1];
+    if (tid < NB) {                                           // isd_j = 1/sqrt(a_jj), d_j = a_jj * isd_j
+        const double ajj = sm.dg[tid];
+        if (!(ajj > 0.0) || isinf(ajj)) {                     // report the first bad pivot (1-based)
+            const int idx = g.kblk * NB + tid + 1;
+            if (atomicCAS(g.info + mat, 0, idx) != 0) atomicMin(g.info + mat, idx);
+        }
+        const double isd = rsqrt(ajj);
+        isd_s[tid] = isd;
+        d_s[tid] = ajj * isd;
+    }
+    __syncthreads();
+    double* W = g.w ? g.w + mat * g.strideW + (int64_t)g.kblk * NB * (g.ldw + 1) : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = 4 * ty + i;
+        const double isd_row = isd_s[row];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int cc = 4 * tx + c;
+            if (active && cc <= row) A[(int64_t)row * g.lda + cc] = (cc == row) ? d_s[row] : a[i][c] * isd_s[cc];
+            if (W) W[(int64_t)row * g.ldw + cc] = (active && cc <= row) ? r[i][c] * isd_row : 0.0;
+        }
+    }
+    if (tid < 32 && g.logdet) {   // log det = sum log a_jj (= 2 sum log d_j), fixed order
+        double s = log(sm.dg[tid]) + log(sm.dg[tid + 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) g.logdet[mat] += s;
+    }
+}
+
+__global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
+    __shared__ __align__(16) DiagSmem sm;
+    chol_diag_block(g, (int)blockIdx.x, sm);
+}
+
+#ifdef BOGP_DIAG_BENCH
+struct DiagSmemV2 {
     double col[2][kDiagNB];    // u_i = a[i][j] before scaling (rows > j)
     double col2[2][kDiagNB];   // u_i / a_jj
     double xrow[2][kDiagNB];   // R[j][c]  (unscaled row j of the inverse)
@@ -36,7 +208,7 @@ struct DiagSmem {
 };
 
 // Device body: factor + invert block `kblk` of matrix `mat`; 256 threads; `sm` in shared memory.
-__device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, DiagSmem& sm) {
+__device__ __forceinline__ void chol_diag_block_v2(const DiagArgs& g, int mat, DiagSmemV2& sm) {
     constexpr int NB = kDiagNB;
     double (&col)[2][NB] = sm.col; double (&col2)[2][NB] = sm.col2; double (&xrow)[2][NB] = sm.xrow; double (&dg)[NB] = sm.dg;
     const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15, lane = tid & 31;
@@ -137,12 +309,11 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
     }
 }
 
-__global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
-    __shared__ __align__(16) DiagSmem sm;
-    chol_diag_block(g, (int)blockIdx.x, sm);
+__global__ void __launch_bounds__(256) chol_diag_kernel_v2(DiagArgs g) {
+    __shared__ __align__(16) DiagSmemV2 sm;
+    chol_diag_block_v2(g, (int)blockIdx.x, sm);
 }
 
-#ifdef BOGP_DIAG_BENCH
 __global__ void __launch_bounds__(256) chol_diag_kernel_v1(DiagArgs g) {
     constexpr int NB = kDiagNB;
     __shared__ __align__(16) double col[2][NB];    // u_i = a[i][j] before scaling (rows > j)

@@ -16,13 +16,13 @@ int main() {
     cudaMemset(ld, 0, 8); cudaMemset(info, 0, 4);
     DiagArgs g{a, n, 0, w, n, 0, ld, info, 0};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int variant = 0; variant < 2; variant++) {
+    for (int variant = 0; variant < 3; variant++) {
         float best = 1e9;
         for (int rep = 0; rep < 20; rep++) {
             cudaMemcpy(a, a0, n * n * 8, cudaMemcpyDeviceToDevice);
             cudaDeviceSynchronize();
             cudaEventRecord(e0);
-            if (variant == 0) chol_diag_kernel_v1<<<1, 256>>>(g); else chol_diag_kernel<<<1, 256>>>(g);
+            if (variant == 0) chol_diag_kernel_v1<<<1, 256>>>(g); else if (variant == 1) chol_diag_kernel_v2<<<1, 256>>>(g); else chol_diag_kernel<<<1, 256>>>(g);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
         }
