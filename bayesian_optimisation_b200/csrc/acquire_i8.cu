@@ -15,12 +15,12 @@
 // Because the integer sums are exact, V does not depend on any summation order: the result is
 // bit-reproducible across tiles, chunks and GPUs by construction.
 //
-// Kernel structure (one CTA = 128 rows of W x 64 candidates, 192 threads):
+// Kernel structure (one CTA = 128 rows of W x 64 candidates, 320 threads):
 //   warp 0   : bulk-TMA producer  (W digit tile 28 KB + panel digit tile 14 KB per K=32 stage, mbarrier ring)
 //   warp 1   : tcgen05.mma issuer (11 MMAs per stage: slice p of W against slices 0..min(6,7-p) of the
 //              panel concatenated along N, landing on TMEM columns 64(p+q)..: the 8 levels fill all 512 columns)
-//   warps 2-5: epilogue -- tcgen05.ld the 8 int32 levels, Horner-combine them in fp64, scale by the row
-//              exponent, square and reduce over the 128 rows (warp shuffles + shared memory).
+//   warps 2-9: epilogue -- tcgen05.ld the 8 int32 levels, Horner-combine them in fp64, scale by the row
+//              exponent, square and reduce over the 128 rows (transposing warp butterfly + shared memory).
 #include "common.cuh"
 #include "fit.cuh"
 
@@ -269,17 +269,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
-    const uint32_t z = 0u;
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "r"(taddr), "r"(z) : "memory");
-}
 
 struct TriI8Args {
     const uint8_t* wq; const uint8_t* panel; const double* wscale; double* qpart;
     int nI, nct, n_pad; int64_t S; int b_signed; int group;   // group = candidate tiles scheduled together (L2 reuse of the panel)
 };
 
-__global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
+// int32 (held as raw bits) -> double without the conversion unit: 2^52 + 2^31 + r is exact in the
+// low mantissa bits, and subtracting the constant is exact.
+__device__ __forceinline__ double i32_bits_to_f64(uint32_t r) {
+    return __hiloint2double(0x43300000, (int)(r ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+constexpr int kI8Threads = 320;      // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+
+__global__ void __launch_bounds__(kI8Threads, 1) trigemm_i8_kernel(TriI8Args g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full   = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kI8Stages * kI8Stage);
     uint64_t* empt   = full + kI8Stages;
@@ -297,11 +301,21 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
     const int ct = grp * g.group + rem % gc;
     if (ib < 0) return;                                           // padding CTAs of the last (partial) group
     const int nk = (ib + 1) * (kI8BM / kI8KB);
+    const uint8_t* wsrc = g.wq + (int64_t)ib * (ib + 1) / 2 * (kI8BM / kI8KB) * kI8ATile;
+    const uint8_t* psrc = g.panel + (int64_t)ct * (g.n_pad / kI8KB) * kI8BTile;
+    const int npre = nk < kI8Stages ? nk : kI8Stages;             // stages filled before anybody has to free one
 
     if (tid == 0) {
         for (int s = 0; s < kI8Stages; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 1); }
         mbar_init(accbar, 1);
         fence_mbar_init();
+        // the first loads leave now, so that their latency overlaps the TMEM allocation and the barrier below
+        for (int kt = 0; kt < npre; kt++) {
+            unsigned char* dst = smem_raw + (size_t)kt * kI8Stage;
+            mbar_expect_tx(&full[kt], kI8Stage);
+            bulk_g2s(dst, wsrc + (int64_t)kt * kI8ATile, kI8ATile, &full[kt]);
+            bulk_g2s(dst + kI8ATile, psrc + (int64_t)kt * kI8BTile, kI8BTile, &full[kt]);
+        }
     }
     if (warp == 1) {                                              // TMEM: all 512 columns (8 levels x 64 candidates)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
@@ -312,23 +326,11 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 2) {   // level 7 is first touched by an accumulating MMA: zero it.  Levels 0..6 are initialised
-                       // by the first (non-accumulating) MMAs of slice 0.
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        for (int c = 7 * kI8BN; c < 8 * kI8BN; c += 8) tmem_st8_zero(tmem + lane_base + c);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
     if (warp == 0) {
         if (lane == 0) {
-            const uint8_t* wsrc = g.wq + (int64_t)ib * (ib + 1) / 2 * (kI8BM / kI8KB) * kI8ATile;
-            const uint8_t* psrc = g.panel + (int64_t)ct * (g.n_pad / kI8KB) * kI8BTile;
-            for (int kt = 0; kt < nk; kt++) {
+            for (int kt = npre; kt < nk; kt++) {
                 const int s = kt % kI8Stages;
-                if (kt >= kI8Stages) mbar_wait(&empt[s], ((kt / kI8Stages) - 1) & 1);
+                mbar_wait(&empt[s], ((kt / kI8Stages) - 1) & 1);
                 unsigned char* dst = smem_raw + (size_t)s * kI8Stage;
                 mbar_expect_tx(&full[s], kI8Stage);
                 bulk_g2s(dst, wsrc + (int64_t)kt * kI8ATile, kI8ATile, &full[s]);
@@ -352,7 +354,16 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
                     for (int n0 = 0; n0 < ntot; n0 += 256) {
                         const int nn = (ntot - n0) < 256 ? (ntot - n0) : 256;
                         const uint64_t db = umma_desc_kmajor(b0 + n0 * 16, kI8Slices * kI8BN * 16, 128);
-                        umma_i8(tmem + (uint32_t)(p * kI8BN + n0), da, db, umma_idesc_i8(kI8BM, nn, g.b_signed), (p > 0 || kt > 0) ? 1u : 0u);
+                        if (p == 1 && n0 == 256 && kt == 0) {
+                            // Levels 0..6 are initialised by the non-accumulating MMAs of slice 0; level 7 is first
+                            // written here (slice 1 x panel slice 6), so in the very first stage that part is split off
+                            // and does not accumulate.  No TMEM zeroing pass is needed.
+                            umma_i8(tmem + (uint32_t)(p * kI8BN + n0), da, db, umma_idesc_i8(kI8BM, nn - kI8BN, g.b_signed), 1u);
+                            const uint64_t db7 = umma_desc_kmajor(b0 + (n0 + nn - kI8BN) * 16, kI8Slices * kI8BN * 16, 128);
+                            umma_i8(tmem + (uint32_t)(p * kI8BN + n0 + nn - kI8BN), da, db7, umma_idesc_i8(kI8BM, kI8BN, g.b_signed), 0u);
+                        } else {
+                            umma_i8(tmem + (uint32_t)(p * kI8BN + n0), da, db, umma_idesc_i8(kI8BM, nn, g.b_signed), (p > 0 || kt > 0) ? 1u : 0u);
+                        }
                     }
                 }
                 umma_commit(&empt[s]);                            // stage reusable once these MMAs have read it
@@ -360,34 +371,52 @@ __global__ void __launch_bounds__(192, 1) trigemm_i8_kernel(TriI8Args g) {
             umma_commit(accbar);                                  // all MMAs done -> epilogue
         }
     } else {
+        // Epilogue, 8 warps: warp w reads TMEM lane quarter w % 4 (hardware rule) and half (w-2)/4 of the 64 candidates.
+        // Two warps per lane quarter keep TMEM loads of one in flight while the other one computes.
         mbar_wait(accbar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q4 = warp & 3;                                  // TMEM lane quarter this warp may read
+        const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         const double scale = g.wscale[ib * kI8BM + q4 * 32 + lane];
-        for (int c0 = 0; c0 < kI8BN; c0 += 8) {
+        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+        const int csel = (b4 ? 4 : 0) | (b3 ? 2 : 0) | (b2 ? 1 : 0);
+        for (int c0 = half * (kI8BN / 2); c0 < (half + 1) * (kI8BN / 2); c0 += 8) {
             uint32_t r[8][8];
 #pragma unroll
             for (int t = 0; t < 8; t++) tmem_ld8(tmem + lane_base + t * kI8BN + c0, r[t]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            double acc[8];
+            double v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                double a = (double)(int)r[7][j];
+                double a = i32_bits_to_f64(r[7][j]);
 #pragma unroll
-                for (int t = 6; t >= 0; t--) a = fma(a, 0.00390625, (double)(int)r[t][j]);      // Horner in 2^-8 (exact products)
-                acc[j] = a;
+                for (int t = 6; t >= 0; t--) a = fma(a, 0.00390625, i32_bits_to_f64(r[t][j]));      // Horner in 2^-8 (exact products)
+                a *= scale;
+                v[j] = a * a;
+            }
+            // sum over the 32 rows of this warp for 8 columns at once: a transposing butterfly (each step halves the
+            // number of columns a lane carries), then two plain steps.  Fixed order, same on every tile.
+            double w4[4], w2[2], w1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+                w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const double v = acc[j] * scale;
-                double s = v * v;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) red[q4 * kI8BN + c0 + j] = s;
+            for (int i = 0; i < 2; i++) {
+                const double keep = b3 ? w4[i + 2] : w4[i], send = b3 ? w4[i] : w4[i + 2];
+                w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
+            {
+                const double keep = b2 ? w2[1] : w2[0], send = b2 ? w2[0] : w2[1];
+                w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+            if ((lane & 3) == 0) red[q4 * kI8BN + c0 + csel] = w1;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int e = tid - 64;
         if (e < kI8BN) {
             const double q = ((red[e] + red[kI8BN + e]) + red[2 * kI8BN + e]) + red[3 * kI8BN + e];
@@ -450,7 +479,7 @@ int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
     group = group < 1 ? 1 : (group > 64 ? 64 : group);
     const int ngroups = (nct + group - 1) / group;
     TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S, ub ? 0 : 1, group};
-    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<ngroups * nI * group, 192, kI8Smem, stream>>>(ta)));
+    BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<ngroups * nI * group, kI8Threads, kI8Smem, stream>>>(ta)));
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }

@@ -235,8 +235,8 @@ class GPEngine:
         total = int(cd.c_total)
         c_end = total if c_end is None else int(c_end)
         count = c_end - int(c_begin)
-        if chunk is None:      # candidates per kernel chunk: a k_* panel of about 512 MB
-            chunk = min(65536, max(8192, (512 << 20) // (fit.n_pad * 8)))
+        if chunk is None:      # candidates per kernel chunk: a k_* panel of about 2 GB (fewer, longer launches: shorter tails)
+            chunk = min(65536, max(8192, (2 << 30) // (fit.n_pad * 8)))
         chunk = max(64, min(int(chunk), (count + 63) // 64 * 64))
         need = self.lib.bogp_acquire_workspace_bytes(fit._h, chunk)
         if self._acq_ws is None or self._acq_ws.numel() < need:
