@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cands", type=int, default=1 << 20, help="candidates per step per GPU")
-    ap.add_argument("--chunk", type=int, default=32768, help="candidates per kernel chunk")
+    ap.add_argument("--chunk", type=int, default=65536, help="candidates per kernel chunk (two half-chunks are pipelined)")
     ap.add_argument("--e2e-cands", type=int, default=1 << 20)
     ap.add_argument("--ref-sample", type=int, default=8192, help="candidates per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
