@@ -379,6 +379,10 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
     // the int32 level sums of the digit-slice product are overflow-free up to K = 16384 (7 * K * 2^14 < 2^31);
     // larger systems take the fp64 path
     const bool use_i8 = ctx->acquire_path == BOGP_PATH_INT8_TCGEN05 && n_pad <= 16384;
+    {   // the fit packs W for the path selected at fit time; a later switch packs on first use
+        const int prc = fit_ensure_packed(ctx, fit, use_i8 ? BOGP_PATH_INT8_TCGEN05 : BOGP_PATH_FP64_DMMA);
+        if (prc) return prc;
+    }
     auto finish_chunk = [&](int64_t c0, int64_t cur, int64_t Sb, const double* qp, const double* mp, int nIq) -> int {
         const int nfb = (int)((cur + 255) / 256);
         if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }

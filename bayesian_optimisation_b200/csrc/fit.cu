@@ -630,35 +630,54 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
     if (lane == 0) v[row] = s;
 }
 
-// alpha_j = sum_{i >= j} W[i][j] v[i]; block = 32 columns x 8 row-slices, slices combined in order.
-__global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restrict__ w, int64_t ldw, int64_t strideW,
-                                                           const double* __restrict__ v, double* __restrict__ alpha, int n) {
-    __shared__ double part[8][33];
-    w += blockIdx.y * strideW; v += (int64_t)blockIdx.y * n; alpha += (int64_t)blockIdx.y * n;
-    const int col = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32;
-    const int rows = n - c0, per = (rows + 7) / 8;
-    const int rb = c0 + sl * per, re = min(n, rb + per);
+// alpha_j = sum_{i >= j} W[i][j] v[i] in two stages with a fixed summation order.
+// Stage 1: CTA (cb, rc) = 32 columns x 256 rows (8 warps x 32 rows, lane = column: 256-byte row segments);
+//          the 8 warp sums are combined in order -> part[rc][col].  Tiles above the diagonal are skipped.
+// Stage 2: alpha[col] = sum over row chunks rc >= col / 256, ascending.
+constexpr int kTrmvRows = 256;
+__global__ void __launch_bounds__(256) trmv_lower_t_part_kernel(const double* __restrict__ w, int64_t ldw, int64_t strideW,
+                                                                const double* __restrict__ v, double* __restrict__ part, int n, int nrc) {
+    __shared__ double sm[8][33];
+    const int cb = blockIdx.x, rc = blockIdx.y, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int c0 = cb * 32, r0 = rc * kTrmvRows;
+    if (r0 + kTrmvRows <= c0) return;                              // entirely above the diagonal
+    w += blockIdx.z * strideW; v += (int64_t)blockIdx.z * n; part += (int64_t)blockIdx.z * nrc * n;
+    const int col = c0 + lane;
+    const int rb = r0 + wp * 32, re = min(n, rb + 32);
     double s = 0.0;
     if (col < n) {
 #pragma unroll 8
         for (int i = max(rb, col); i < re; i++) s += w[(int64_t)i * ldw + col] * v[i];
     }
-    part[sl][threadIdx.x & 31] = s;
+    sm[wp][lane] = s;
     __syncthreads();
-    if (sl == 0 && col < n) {
+    if (wp == 0 && col < n) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t += part[k][threadIdx.x];
-        alpha[col] = t;
+        for (int k = 0; k < 8; k++) t += sm[k][lane];
+        part[(int64_t)rc * n + col] = t;
     }
 }
+__global__ void __launch_bounds__(256) trmv_lower_t_sum_kernel(const double* __restrict__ part, double* __restrict__ alpha, int n, int nrc) {
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col >= n) return;
+    part += (int64_t)blockIdx.y * nrc * n; alpha += (int64_t)blockIdx.y * n;
+    double t = 0.0;
+    for (int rc = col / kTrmvRows; rc < nrc; rc++) t += part[(int64_t)rc * n + col];
+    alpha[col] = t;
+}
 
+size_t alpha_scratch_doubles(int64_t n) { return (size_t)((n + kTrmvRows - 1) / kTrmvRows) * (size_t)n; }
+
+// d_part: alpha_scratch_doubles(n) doubles per batch entry
 int launch_alpha(bogp_ctx* ctx, const double* d_w, int64_t ldw, int64_t strideW, const double* d_y, double* d_v,
-                 double* d_alpha, int n, int batch) {
+                 double* d_alpha, double* d_part, int n, int batch) {
     trmv_lower_kernel<<<dim3((unsigned)((n + 7) / 8), batch), 256, 0, ctx->stream>>>(d_w, ldw, strideW, d_y, d_v, n);
     BOGP_LAUNCH_CHECK(ctx);
-    trmv_lower_t_kernel<<<dim3((unsigned)((n + 31) / 32), batch), 256, 0, ctx->stream>>>(d_w, ldw, strideW, d_v, d_alpha, n);
+    const int nrc = (n + kTrmvRows - 1) / kTrmvRows;
+    trmv_lower_t_part_kernel<<<dim3((unsigned)((n + 31) / 32), nrc, batch), 256, 0, ctx->stream>>>(d_w, ldw, strideW, d_v, d_part, n, nrc);
+    BOGP_LAUNCH_CHECK(ctx);
+    trmv_lower_t_sum_kernel<<<dim3((unsigned)((n + 255) / 256), batch), 256, 0, ctx->stream>>>(d_part, d_alpha, n, nrc);
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }
@@ -733,11 +752,13 @@ struct bogp_fit {
     int* info;
     double jitter;
     bogp_ctx* ctx;
+    double* apart;                 // partial sums of the transposed triangular product (launch_alpha)
+    bool wp_ready, wq_ready;       // which operand packings of W exist (fit_ensure_packed)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct FitLayout { size_t x, y, ell, a, w, wp, alpha, v, scal, info, wq, wexp, wscale, total; };
+struct FitLayout { size_t x, y, ell, a, w, wp, alpha, v, apart, scal, info, wq, wexp, wscale, total; };
 static FitLayout fit_layout(int64_t n, int dim) {
     const int64_t np = (n + kPad - 1) / kPad * kPad;
     FitLayout l{}; size_t off = 0;
@@ -748,7 +769,7 @@ static FitLayout fit_layout(int64_t n, int dim) {
     // the trtri scratch and the packed W are never live at the same time -> but keep them
     // separate when the scratch is the larger one (ragged block counts)
     l.wp = take((shared > tneed ? shared : tneed) * 8);
-    l.alpha = take(np * 8); l.v = take(np * 8); l.scal = take(64 * 8); l.info = take(64 * 4);
+    l.alpha = take(np * 8); l.v = take(np * 8); l.apart = take(alpha_scratch_doubles(np) * 8); l.scal = take(64 * 8); l.info = take(64 * 4);
     l.wq = take(i8_wq_bytes(np)); l.wexp = take(np * 4); l.wscale = take(np * 8);
     l.total = off;
     return l;
@@ -828,34 +849,42 @@ static int fit_enqueue(bogp_ctx* ctx, const double* d_x, const double* d_y, int6
     f->x_pad = (double*)(base + l.x); f->y_pad = (double*)(base + l.y); f->inv_ell2 = (double*)(base + l.ell);
     f->a = (double*)(base + l.a); f->w = (double*)(base + l.w); f->wp = (double*)(base + l.wp); f->t = f->wp;
     f->wq = (uint8_t*)(base + l.wq); f->wexp = (int*)(base + l.wexp); f->wscale = (double*)(base + l.wscale);
-    f->alpha = (double*)(base + l.alpha); f->v = (double*)(base + l.v); f->scalars = (double*)(base + l.scal); f->info = (int*)(base + l.info);
+    f->alpha = (double*)(base + l.alpha); f->v = (double*)(base + l.v); f->apart = (double*)(base + l.apart); f->scalars = (double*)(base + l.scal); f->info = (int*)(base + l.info);
     cudaStream_t st = ctx->stream;
     int rc;
 #define FIT_TRY(e) do { rc = (e); if (rc) { delete f; return rc; } } while (0)
 #define FIT_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s: %s", #e, cudaGetErrorString(_e)); delete f; return BOGP_ERR_CUDA; } } while (0)
     FIT_CUDA(cudaMemsetAsync(f->scalars, 0, 64 * 8, st));
     FIT_CUDA(cudaMemsetAsync(f->info, 0, 64 * 4, st));
-    FIT_CUDA(cudaMemsetAsync(f->w, 0, (size_t)np * np * 8, st));
+    // W is cleared on the third stream while the Gram matrix is built
+    FIT_CUDA(cudaEventRecord(ctx->ev_aux2, st));
+    FIT_CUDA(cudaStreamWaitEvent(ctx->aux2_stream, ctx->ev_aux2, 0));
+    FIT_CUDA(cudaMemsetAsync(f->w, 0, (size_t)np * np * 8, ctx->aux2_stream));
+    FIT_CUDA(cudaEventRecord(ctx->ev_aux2, ctx->aux2_stream));
     pad_copy_kernel<<<(unsigned)((np * dim + 255) / 256), 256, 0, st>>>(d_x, f->x_pad, n, np, dim); ctx->launches++;
     pad_copy_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(d_y, f->y_pad, n, np, 1); ctx->launches++;
     FIT_TRY(launch_inv_ell2(ctx, d_ell, f->inv_ell2, dim));
     // K1 (lower tiles; identity in the padding)
     FIT_TRY(launch_gram(ctx, f->x_pad, np, n, f->x_pad, np, n, dim, f->inv_ell2, jitter, f->a, np, true, 1, 0));
+    FIT_CUDA(cudaStreamWaitEvent(st, ctx->ev_aux2, 0));
     // K2
     int64_t w_level = 0;     // block size up to which W = L^-1 is already complete
     FIT_TRY(cholesky_blocked(ctx, f->a, np, np, 0, f->w, np, 0, f->scalars, f->info, 1, f->t, 0, &w_level));
     if (w_level < np) FIT_TRY(trtri_recursive(ctx, f->a, np, 0, f->w, np, 0, f->t, 0, np, 1, w_level < 256 ? 256 : w_level));
-    // alpha = W^T W y
-    FIT_TRY(launch_alpha(ctx, f->w, np, 0, f->y_pad, f->v, f->alpha, (int)np, 1));
-    nlml_finish_kernel<<<1, 256, 0, st>>>(f->y_pad, f->alpha, (int)np, (int)n, f->scalars); ctx->launches++;
-    // packed W (overwrites the trtri scratch)
+    // W is final.  Its operand packing for the selected tensor path (which overwrites the trtri scratch) goes to
+    // the third stream, next to alpha = W^T W y and the marginal likelihood on this one.
+    f->wp_ready = f->wq_ready = false;
+    FIT_CUDA(cudaEventRecord(ctx->ev_aux2, st));
+    FIT_CUDA(cudaStreamWaitEvent(ctx->aux2_stream, ctx->ev_aux2, 0));
     {
-        const int nI = (int)(np / kAcqBM);
-        dim3 grid(nI * (kAcqBM / kAcqKB), nI);
-        pack_w_kernel<<<grid, 256, 0, st>>>(f->w, np, f->wp); ctx->launches++;
+        StreamSwap sw(ctx, ctx->aux2_stream);
+        const int path = (ctx->acquire_path == BOGP_PATH_INT8_TCGEN05 && np <= 16384) ? BOGP_PATH_INT8_TCGEN05 : BOGP_PATH_FP64_DMMA;
+        FIT_TRY(fit_ensure_packed(ctx, f, path));
     }
-    // digit tiles of W for the INT8 tensor path
-    FIT_TRY(launch_slice_w(ctx, f->w, np, f->wexp, f->wscale, f->wq));
+    FIT_CUDA(cudaEventRecord(ctx->ev_aux2, ctx->aux2_stream));
+    FIT_TRY(launch_alpha(ctx, f->w, np, 0, f->y_pad, f->v, f->alpha, f->apart, (int)np, 1));
+    nlml_finish_kernel<<<1, 256, 0, st>>>(f->y_pad, f->alpha, (int)np, (int)n, f->scalars); ctx->launches++;
+    FIT_CUDA(cudaStreamWaitEvent(st, ctx->ev_aux2, 0));
     FIT_CUDA(cudaGetLastError());
     *out = f;
     return BOGP_OK;
@@ -878,6 +907,23 @@ extern "C" double bogp_fit_logdet(const bogp_fit* fit) {
 
 // accessors used by acquire.cu
 namespace bogp {
+int fit_ensure_packed(bogp_ctx* ctx, const bogp_fit* cf, int path) {
+    bogp_fit* f = const_cast<bogp_fit*>(cf);
+    const int64_t np = f->n_pad;
+    if (path == BOGP_PATH_INT8_TCGEN05) {
+        if (f->wq_ready) return BOGP_OK;
+        int rc = launch_slice_w(ctx, f->w, np, f->wexp, f->wscale, f->wq);      // digit tiles of W for the INT8 tensor path
+        if (rc) return rc;
+        f->wq_ready = true;
+    } else {
+        if (f->wp_ready) return BOGP_OK;
+        const int nI = (int)(np / kAcqBM);
+        pack_w_kernel<<<dim3(nI * (kAcqBM / kAcqKB), nI), 256, 0, ctx->stream>>>(f->w, np, f->wp);   // fragment-packed W for the DMMA path
+        BOGP_LAUNCH_CHECK(ctx);
+        f->wp_ready = true;
+    }
+    return BOGP_OK;
+}
 const double* fit_wp(const bogp_fit* f) { return f->wp; }
 const uint8_t* fit_wq(const bogp_fit* f) { return f->wq; }
 const double* fit_wscale(const bogp_fit* f) { return f->wscale; }

@@ -11,7 +11,8 @@ int launch_gram(bogp_ctx* ctx, const double* d_a, int64_t na, int64_t na_valid, 
                 bool lower_tiles_only, int batch, int64_t strideK);
 int launch_inv_ell2(bogp_ctx* ctx, const double* d_ell, double* d_out, int64_t count);
 int launch_alpha(bogp_ctx* ctx, const double* d_w, int64_t ldw, int64_t strideW, const double* d_y, double* d_v,
-                 double* d_alpha, int n, int batch);
+                 double* d_alpha, double* d_part, int n, int batch);
+size_t alpha_scratch_doubles(int64_t n);
 
 int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
                      int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT, int64_t* w_level = nullptr);
@@ -43,6 +44,9 @@ const uint8_t* fit_wq(const bogp_fit* f);
 const double* fit_wscale(const bogp_fit* f);
 
 const double* fit_wp(const bogp_fit* f);
+// Operand packing of W for the given tensor path, if the fit has not done it yet (the fit packs for the path that
+// is selected when it runs; the other packing is made on first use).  Enqueued on ctx->stream.
+int fit_ensure_packed(bogp_ctx* ctx, const bogp_fit* f, int path);
 const double* fit_xpad(const bogp_fit* f);
 const double* fit_inv_ell2(const bogp_fit* f);
 const double* fit_alpha(const bogp_fit* f);

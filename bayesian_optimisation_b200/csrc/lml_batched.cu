@@ -228,7 +228,7 @@ __global__ void pad_copy2_kernel(const double* __restrict__ src, double* __restr
     dst[i] = (i / width < n) ? src[i] : 0.0;
 }
 
-struct LmlLayout { size_t x, y, il, a, w, t, alpha, v, logdet, info, gpart, total; int64_t n_pad; size_t tper; };
+struct LmlLayout { size_t x, y, il, a, w, t, alpha, v, apart, logdet, info, gpart, total; int64_t n_pad; size_t tper; };
 static LmlLayout lml_layout(int64_t n, int dim, int64_t R, int want_grad) {
     LmlLayout l{}; size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
@@ -237,7 +237,8 @@ static LmlLayout lml_layout(int64_t n, int dim, int64_t R, int want_grad) {
     l.tper = cholesky_scratch_doubles(np);
     l.x = take(np * dim * 8); l.y = take(np * 8); l.il = take(R * dim * 8);
     l.a = take((size_t)R * np * np * 8); l.w = take((size_t)R * np * np * 8); l.t = take((size_t)R * l.tper * 8);
-    l.alpha = take(R * np * 8); l.v = take(R * np * 8); l.logdet = take(R * 8); l.info = take(R * 4);
+    l.alpha = take(R * np * 8); l.v = take(R * np * 8); l.apart = take((size_t)R * alpha_scratch_doubles(np) * 8);
+    l.logdet = take(R * 8); l.info = take(R * 4);
     l.gpart = take(want_grad ? (size_t)R * ((np / 64) * (np / 64 + 1) / 2) * dim * 8 : 8);
     l.total = off;
     return l;
@@ -278,7 +279,7 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
     double* x_pad = (double*)(base + l.x); double* y_pad = (double*)(base + l.y); double* il = (double*)(base + l.il);
     double* A = (double*)(base + l.a); double* W = (double*)(base + l.w); double* T = (double*)(base + l.t);
     double* alpha = (double*)(base + l.alpha); double* v = (double*)(base + l.v); double* logdet = (double*)(base + l.logdet);
-    double* gpart = (double*)(base + l.gpart);
+    double* gpart = (double*)(base + l.gpart); double* apart = (double*)(base + l.apart);
     const int64_t mat = np * np;
     pad_copy2_kernel<<<(unsigned)((np * dim + 255) / 256), 256, 0, st>>>(d_x, x_pad, n, np, dim); BOGP_LAUNCH_CHECK(ctx);
     pad_copy2_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(d_y, y_pad, n, np, 1); BOGP_LAUNCH_CHECK(ctx);
@@ -292,7 +293,7 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
         rc = launch_gram(ctx, x_pad, np, n, x_pad, np, n, dim, il + r0 * dim, jitter, Ab, np, true, rb, mat); if (rc) return rc;
         rc = cholesky_blocked(ctx, Ab, np, np, mat, Wb, np, mat, logdet + r0, info + r0, rb, T + r0 * l.tper, (int64_t)l.tper); if (rc) return rc;
         rc = trtri_recursive(ctx, Ab, np, mat, Wb, np, mat, T + r0 * l.tper, (int64_t)l.tper, np, rb, 256); if (rc) return rc;
-        rc = launch_alpha(ctx, Wb, np, mat, y_pad, v + r0 * np, alpha + r0 * np, (int)np, rb); if (rc) return rc;
+        rc = launch_alpha(ctx, Wb, np, mat, y_pad, v + r0 * np, alpha + r0 * np, apart + r0 * alpha_scratch_doubles(np), (int)np, rb); if (rc) return rc;
         if (d_grad_out) {
             GemmArgs k{};   // Kinv = W^T W (lower part) into A (L is dead)
             k.A = Wb; k.lda = np; k.strideA = mat; k.B = Wb; k.ldb = np; k.strideB = mat; k.C = Ab; k.ldc = np; k.strideC = mat;
