@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) panel_kernel(PanelArgs p) {
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < DIMP; k++) { const double df = pc[k] - xs[k][jl]; s += (df * df) * il[k]; }
-        double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
+        double v = (j < p.n) ? exp_nonpos(-0.5 * s) : 0.0;
         if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
         mu += al[jl] * v;
         // tile kt = jb*16 + t/4, kk = t%4, n8 = warp

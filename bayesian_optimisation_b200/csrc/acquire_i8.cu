@@ -128,12 +128,29 @@ __device__ __forceinline__ void transpose4x4_bytes(uint32_t w0, uint32_t w1, uin
 // UB = false: balanced signed digits (|digit| <= 128), safe up to n_pad = 16384.
 // DIMP = feature count rounded up to an instantiated size; the extra dimensions carry zeros
 // (coordinate 0, 1/ell^2 = 0) and add exactly +0 to the squared distance.
+// k_*(x_j, p) for one row of the shared x block ([row][DIMP], read with 16-byte broadcast loads); same operation
+// order as every other kernel-function site (Gram, FP64 panel, LML): s += ((p_k - x_k)^2) / ell_k^2, k ascending.
+template <int DIMP>
+__device__ __forceinline__ double kstar_row(const double (&pc)[DIMP], const double (&il)[DIMP], const double* xrow, const double* etab) {
+    const double2* xr = reinterpret_cast<const double2*>(xrow);
+    double s = 0.0;
+#pragma unroll
+    for (int k2 = 0; k2 < DIMP / 2; k2++) {
+        const double2 xv = xr[k2];
+        const double d0 = pc[2 * k2] - xv.x;     s += (d0 * d0) * il[2 * k2];
+        const double d1 = pc[2 * k2 + 1] - xv.y; s += (d1 * d1) * il[2 * k2 + 1];
+    }
+    return exp_nonpos(-0.5 * s, etab);
+}
+
 template <int DIMP, bool UB>
 __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
+    static_assert(DIMP % 2 == 0, "rows of the x block are read as double2");
     __shared__ __align__(128) double ps_raw[kI8BN * BOGP_MAX_DIM];
-    __shared__ double xs[DIMP][kAcqBM + 1];
+    __shared__ __align__(16) double xs[kAcqBM][DIMP];
     __shared__ double al[kAcqBM];
     __shared__ double sl[BOGP_MAX_DIM];
+    __shared__ double etab[64];
     __shared__ double mured[4][kI8BN];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -156,10 +173,11 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     }
     for (int i = tid; i < kAcqBM * DIMP; i += 256) {
         int r = i / DIMP, k = i % DIMP;
-        xs[k][r] = k < dim ? p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k] : 0.0;
+        xs[r][k] = k < dim ? p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k] : 0.0;
     }
     al[tid] = p.alpha[jb * kAcqBM + tid];
     if (tid < BOGP_MAX_DIM) sl[tid] = tid < dim ? p.inv_ell2[tid] : 0.0;
+    if (tid < 64) etab[tid] = kExp2Tab[tid];
     if (explicit_mode) {
         if (used_tma) mbar_wait(&bar, 0);
         else for (int i = tid; i < nvalid * dim; i += 256) ps_raw[i] = p.cand.points[cbase * dim + i];
@@ -178,7 +196,11 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     double pc[DIMP], il[DIMP];
 #pragma unroll
     for (int k = 0; k < DIMP; k++) { pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0; il[k] = sl[k]; }
-    const int64_t cglob = cbase + nl;
+    const int nvr = p.n - jb * kAcqBM;             // rows of this block that are real measurements (the rest is padding: k_* = 0)
+    // row of this block on which the reference's shape-equality jitter falls for this candidate (-1: none)
+    const int64_t jq64 = (cbase + nl) - (int64_t)jb * kAcqBM;
+    const int jq = (p.cand.cross_jitter != 0.0 && jq64 >= 0 && jq64 < kAcqBM) ? (int)jq64 : -1;
+    const double jit = p.cand.cross_jitter;
     double mu = 0.0;      // this thread's 4 row groups, ascending
     // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
     for (int g = tid >> 6; g < kAcqBM / 16; g += 4) {
@@ -190,12 +212,10 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
                 uint32_t lo[4], hi[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int jl = g * 16 + e4 * 4 + i, j = jb * kAcqBM + jl;
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < DIMP; k++) { const double df = pc[k] - xs[k][jl]; s += (df * df) * il[k]; }
-                    double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
-                    if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
+                    const int jl = g * 16 + e4 * 4 + i;
+                    double v = kstar_row<DIMP>(pc, il, &xs[jl][0], etab);
+                    v = jl < nvr ? v : 0.0;
+                    if (jl == jq) v += jit;
                     mug += al[jl] * v;
                     const unsigned long long fx = __double2ull_rn(v * 18014398509481984.0);   // t = v / 2, fx = t * 2^55 = v * 2^54 (exact scaling)
                     lo[i] = (uint32_t)fx; hi[i] = (uint32_t)(fx >> 32);
@@ -211,12 +231,10 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
             for (int q = 0; q < kI8Slices; q++) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                const int jl = g * 16 + e, j = jb * kAcqBM + jl;
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < DIMP; k++) { const double df = pc[k] - xs[k][jl]; s += (df * df) * il[k]; }
-                double v = (j < p.n) ? exp(-0.5 * s) : 0.0;
-                if (p.cand.cross_jitter != 0.0 && (int64_t)j == cglob) v += p.cand.cross_jitter;
+                const int jl = g * 16 + e;
+                double v = kstar_row<DIMP>(pc, il, &xs[jl][0], etab);
+                v = jl < nvr ? v : 0.0;
+                if (jl == jq) v += jit;
                 mug += al[jl] * v;
                 int d[kI8Slices];
                 balanced_digits(__double2ll_rn(v * 18014398509481984.0), d);   // t = v / 2, fx = t * 2^55 = v * 2^54

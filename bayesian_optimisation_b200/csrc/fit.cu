@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs g) {
         for (int j = 0; j < 4; j++) {
             const int64_t c = c0 + tx * 4 + j;
             const bool pad = (r >= g.na_valid) || (c >= g.nb_valid);
-            double e = pad ? 0.0 : exp(-0.5 * s[i][j]);
+            double e = pad ? 0.0 : exp_nonpos(-0.5 * s[i][j]);
             if (r == c) e = pad ? 1.0 : e + g.jitter;
             v[j] = e;
         }

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) nlml_small_kernel(SmallArgs g) {
         if (j > i) continue;
         double s = 0.0;
         for (int k = 0; k < dim; k++) { const double df = xs[k * 64 + i] - xs[k * 64 + j]; s += (df * df) * il[k]; }
-        double kv = exp(-0.5 * s);
+        double kv = exp_nonpos(-0.5 * s);
         if (i == j) kv += g.jitter;
         a[i * SLD + j] = kv;
     }
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) nlml_small_kernel(SmallArgs g) {
         for (int k = i; k < n; k++) kinv += w[k * SLD + i] * w[k * SLD + j];
         double s = 0.0;
         for (int k = 0; k < dim; k++) { const double df = xs[k * 64 + i] - xs[k * 64 + j]; s += (df * df) * il[k]; }
-        const double c = (al[i] * al[j] - kinv) * exp(-0.5 * s);
+        const double c = (al[i] * al[j] - kinv) * exp_nonpos(-0.5 * s);
 #pragma unroll
         for (int k = 0; k < BOGP_MAX_DIM; k++) if (k < dim) { const double df = xs[k * 64 + i] - xs[k * 64 + j]; acc[k] += c * (df * df); }
     }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) grad_contract_kernel(GradArgs g) {
 #pragma unroll
             for (int k = 0; k < BOGP_MAX_DIM; k++)
                 if (k < dim) { const double df = xi[k][li] - xj[k][lj]; d2[k] = df * df; s += d2[k] * il[k]; }
-            const double c = (ai[li] * aj[lj] - kv[b]) * exp(-0.5 * s);
+            const double c = (ai[li] * aj[lj] - kv[b]) * exp_nonpos(-0.5 * s);
 #pragma unroll
             for (int k = 0; k < BOGP_MAX_DIM; k++) if (k < dim) acc[k] += c * d2[k];
         }
