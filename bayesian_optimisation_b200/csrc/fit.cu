@@ -283,14 +283,49 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
     BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, bs));
     BOGP_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
     int rc = BOGP_OK;
-    // Interleaved triangular inverse (n = 256 * 2^m, n >= 1024, caller asked for it): the recursive-doubling
-    // merges W21 = -W22 (L21 W11) are issued on the bulk stream as soon as their inputs are final -- the
-    // product T = L21 W11 when the left block is complete, the second product when the right block is --
-    // so that only one GEMM per level is left after the last panel.  One T buffer per level.
+    // Interleaved triangular inverse (n >= 1024, caller asked for it), right-looking by block rows of 256:
+    //   W[i, j] = -W_ii * Acc[i, j],   Acc[i, j] = sum_{k=j}^{i-1} L[i, k] W[k, j]      (i > j, blocks)
+    // As soon as block row p of W is complete, its contribution to every later row is added in ONE rank-256
+    // product  Acc[p+1:, :p+1] += L[p+1:, p] * W[p, :p+1]  (the shape of the trailing SYRK: fills idle SMs on the
+    // third stream), so after the last panel only the small product of the last block row remains -- instead of the
+    // serial chain of one merge per level that recursive doubling leaves.  Acc is kept TRANSPOSED in the strictly
+    // upper 256-blocks of A, which the factorisation never touches: Acc[i, j] lives at A[j, i].
+    // Systems beyond 4096 rows are throughput-bound, not latency-bound: there the recursive-doubling merges
+    // W21 = -W22 (L21 W11) (few large products, issued as soon as their inputs are final; needs a power-of-two panel
+    // count) are cheaper than 64 read-modify-write passes over the accumulator.
     const int64_t npan = n / kOuter;
-    const bool interleave = w_level && n >= 1024 && n % kOuter == 0 && (npan & (npan - 1)) == 0;
+    const bool interleave = w_level && n >= 1024 && n % kOuter == 0;
+    static const char* trtri_env = getenv("BOGP_TRTRI");       // experiment switch: "doubling" | "right"
+    const bool want_doubling = trtri_env ? trtri_env[0] == 'd' : n > 4096;     // measured: 4096 4.01 vs 4.42 ms, 8192 21.1 vs 18.6 ms, 16384 142 vs 120 ms
+    const bool doubling = interleave && want_doubling && (npan & (npan - 1)) == 0;
     cudaStream_t ts = ctx->aux2_stream;
-    auto schedule_trtri = [&](int64_t i) -> int {          // panel i (and all bulk work of iteration i) has been enqueued
+    if (interleave && !doubling) {
+        BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, ctx->ev_fork, 0));
+        for (int64_t j = 0; (j + 1) * kOuter < n; j++)       // zero the accumulator blocks
+            BOGP_CUDA_CHECK(cudaMemset2DAsync(d_a + j * kOuter * lda + (j + 1) * kOuter, lda * sizeof(double), 0,
+                                              (size_t)(n - (j + 1) * kOuter) * sizeof(double), kOuter, ts));
+    }
+    auto schedule_rightlooking = [&](int64_t pnl) -> int {        // panel pnl (and all bulk work of its iteration) has been enqueued
+        BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_in, 0));      // W_pp (chain)
+        StreamSwap sw(ctx, ts);
+        const int64_t o = pnl * kOuter;
+        if (pnl > 0) {                                          // block row pnl of W: -W_pp * Acc[p, :p]
+            GemmArgs g2{};
+            g2.A = d_w + o * (ldw + 1); g2.lda = ldw; g2.B = d_a + o; g2.ldb = lda; g2.C = d_w + o * ldw; g2.ldc = ldw;
+            g2.M = kOuter; g2.N = (int)o; g2.K = kOuter; g2.alpha = -1.0;
+            int r = launch_gemm<64, 64, A_MK, B_NK, K_LE_M>(ctx, g2, 1);
+            if (r) return r;
+        }
+        if (o + kOuter < n) {                                   // Acc^T[:p+1, p+1:] += W[p, :p+1]^T * L[p+1:, p]^T
+            BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_dn2, 0)); // L below panel pnl is final (bulk)
+            GemmArgs u{};
+            u.A = d_w + o * ldw; u.lda = ldw; u.B = d_a + (o + kOuter) * lda + o; u.ldb = lda; u.C = d_a + (o + kOuter); u.ldc = lda;
+            u.M = (int)(o + kOuter); u.N = (int)(n - o - kOuter); u.K = kOuter; u.alpha = 1.0; u.accumulate = 1;
+            return launch_gemm<128, 128, A_KM, B_NK, K_ALL>(ctx, u, 1);
+        }
+        return BOGP_OK;
+    };
+    auto schedule_doubling = [&](int64_t i) -> int {          // panel i (and all bulk work of iteration i) has been enqueued
         // third stream: the merges fill idle SMs without delaying the bulk stream (which the chain waits on)
         BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_in, 0));      // W blocks of panel i (chain)
         BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_dn2, 0));     // L rows below panel i are final (bulk)
@@ -317,6 +352,7 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
         }
         return BOGP_OK;
     };
+    auto schedule_trtri = [&](int64_t pnl) -> int { return doubling ? schedule_doubling(pnl) : schedule_rightlooking(pnl); };
     constexpr int kInBlockPhases = 12;                         // barriers per inblock256_kernel launch
     constexpr size_t kInBlockSmem = GemmSmem<64, 64>::bytes > sizeof(DiagSmem) ? GemmSmem<64, 64>::bytes : sizeof(DiagSmem);
     static const bool fused = !(getenv("BOGP_FIT_FUSED") && getenv("BOGP_FIT_FUSED")[0] == '0');
