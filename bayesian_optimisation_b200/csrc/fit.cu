@@ -269,6 +269,8 @@ __global__ void __launch_bounds__(256) inblock256_kernel(InBlockArgs g) {
 // the rest of the tall panel and the trailing SYRK -- runs on the caller's stream, one panel behind.
 // Four events carry the dependencies.  All accumulation orders are the same as in the sequential
 // driver, so the factor is bit-identical.
+__global__ void zero_upper_blocks_kernel(double* __restrict__ a, int64_t lda, int64_t n, int blk);
+
 struct StreamSwap {
     bogp_ctx* c; cudaStream_t saved;
     StreamSwap(bogp_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
@@ -301,9 +303,8 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
     cudaStream_t ts = ctx->aux2_stream;
     if (interleave && !doubling) {
         BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, ctx->ev_fork, 0));
-        for (int64_t j = 0; (j + 1) * kOuter < n; j++)       // zero the accumulator blocks
-            BOGP_CUDA_CHECK(cudaMemset2DAsync(d_a + j * kOuter * lda + (j + 1) * kOuter, lda * sizeof(double), 0,
-                                              (size_t)(n - (j + 1) * kOuter) * sizeof(double), kOuter, ts));
+        zero_upper_blocks_kernel<<<dim3((unsigned)(n / kOuter - 1), 64), 256, 0, ts>>>(d_a, lda, n, kOuter);   // the accumulator blocks
+        BOGP_LAUNCH_CHECK(ctx);
     }
     auto schedule_rightlooking = [&](int64_t pnl) -> int {        // panel pnl (and all bulk work of its iteration) has been enqueued
         BOGP_CUDA_CHECK(cudaStreamWaitEvent(ts, e_in, 0));      // W_pp (chain)
@@ -768,6 +769,27 @@ __global__ void pad_copy_kernel(const double* __restrict__ src, double* __restri
     dst[i] = (i / width < n) ? src[i] : 0.0;
 }
 
+// One launch at the start of a fit: zero-padded copies of X and y, 1/ell^2, cleared status words.
+__global__ void __launch_bounds__(256) fit_prepare_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ ell,
+                                                          double* __restrict__ x_pad, double* __restrict__ y_pad, double* __restrict__ inv_ell2,
+                                                          double* __restrict__ scalars, int* __restrict__ info, int64_t n, int64_t n_pad, int dim) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad * dim) x_pad[i] = (i / dim < n) ? x[i] : 0.0;
+    if (i < n_pad) y_pad[i] = (i < n) ? y[i] : 0.0;
+    if (i < dim) { const double l = ell[i]; inv_ell2[i] = 1.0 / (l * l); }
+    if (i < 64) { scalars[i] = 0.0; info[i] = 0; }
+}
+
+// zero the strictly upper blk x blk blocks of a row-major matrix (accumulators of the interleaved triangular inverse)
+__global__ void __launch_bounds__(256) zero_upper_blocks_kernel(double* __restrict__ a, int64_t lda, int64_t n, int blk) {
+    const int64_t j = blockIdx.x;                      // block row
+    const int64_t c0 = (j + 1) * blk, w2 = (n - c0) / 2;   // columns [c0, n), as double2 (blk and n are even)
+    for (int64_t r = blockIdx.y; r < blk; r += gridDim.y) {
+        double2* row = reinterpret_cast<double2*>(a + (j * blk + r) * lda + c0);
+        for (int64_t c = threadIdx.x; c < w2; c += 256) row[c] = make_double2(0.0, 0.0);
+    }
+}
+
 __global__ void zero_kernel(double* p, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -890,16 +912,13 @@ static int fit_enqueue(bogp_ctx* ctx, const double* d_x, const double* d_y, int6
     int rc;
 #define FIT_TRY(e) do { rc = (e); if (rc) { delete f; return rc; } } while (0)
 #define FIT_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s: %s", #e, cudaGetErrorString(_e)); delete f; return BOGP_ERR_CUDA; } } while (0)
-    FIT_CUDA(cudaMemsetAsync(f->scalars, 0, 64 * 8, st));
-    FIT_CUDA(cudaMemsetAsync(f->info, 0, 64 * 4, st));
     // W is cleared on the third stream while the Gram matrix is built
     FIT_CUDA(cudaEventRecord(ctx->ev_aux2, st));
     FIT_CUDA(cudaStreamWaitEvent(ctx->aux2_stream, ctx->ev_aux2, 0));
     FIT_CUDA(cudaMemsetAsync(f->w, 0, (size_t)np * np * 8, ctx->aux2_stream));
     FIT_CUDA(cudaEventRecord(ctx->ev_aux2, ctx->aux2_stream));
-    pad_copy_kernel<<<(unsigned)((np * dim + 255) / 256), 256, 0, st>>>(d_x, f->x_pad, n, np, dim); ctx->launches++;
-    pad_copy_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(d_y, f->y_pad, n, np, 1); ctx->launches++;
-    FIT_TRY(launch_inv_ell2(ctx, d_ell, f->inv_ell2, dim));
+    fit_prepare_kernel<<<(unsigned)((np * dim + 255) / 256), 256, 0, st>>>(d_x, d_y, d_ell, f->x_pad, f->y_pad, f->inv_ell2, f->scalars, f->info,
+                                                                         n, np, dim); ctx->launches++;
     // K1 (lower tiles; identity in the padding)
     FIT_TRY(launch_gram(ctx, f->x_pad, np, n, f->x_pad, np, n, dim, f->inv_ell2, jitter, f->a, np, true, 1, 0));
     FIT_CUDA(cudaStreamWaitEvent(st, ctx->ev_aux2, 0));
