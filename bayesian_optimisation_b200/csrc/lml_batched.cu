@@ -131,73 +131,91 @@ __global__ void __launch_bounds__(256) nlml_small_kernel(SmallArgs g) {
 // ------------------------------------------------------------------------------------------------
 // large path pieces
 // ------------------------------------------------------------------------------------------------
-// gpart[r][tile][k] = sum over the pairs (i > j) of one 64x64 tile of
+// gpart[r][bi][k] = sum over the pairs (i > j) of block row bi (64 rows, tiles bj = 0..bi) of
 //   (alpha_i alpha_j - Kinv_ij) k_ij (x_ik - x_jk)^2.
-// grid (lower tiles, restarts); 256 threads, 4x4 pairs per thread, coordinates staged in shared
-// memory, fixed-order block reduction.
+// grid (64-row blocks, restarts); 256 threads, 4x4 pairs per thread and tile, the CTA walks the tiles of its block
+// row (row coordinates staged once, column coordinates per tile), ONE fixed-order block reduction at the end.
+// Templated on the padded feature count: no predicated work on absent dimensions.
 struct GradArgs {
     const double* x_pad; const double* inv_ell2; const double* alpha; const double* kinv;
-    double* gpart; int n, n_pad, dim, ntiles;
+    double* gpart; int n, n_pad, dim, nrb;
 };
 
-__global__ void __launch_bounds__(256) grad_contract_kernel(GradArgs g) {
-    __shared__ double xi[BOGP_MAX_DIM][64], xj[BOGP_MAX_DIM][64];
-    __shared__ double ai[64], aj[64], il[BOGP_MAX_DIM];
-    __shared__ double red[8][BOGP_MAX_DIM];
+template <int DIMP>
+__global__ void __launch_bounds__(256, 2) grad_contract_kernel(GradArgs g) {
+    __shared__ __align__(16) double xi[DIMP][64], xj[DIMP][64];
+    __shared__ __align__(16) double ai[64], aj[64], ils[DIMP], etab[64];
+    __shared__ double red[8][DIMP];
     const int tid = threadIdx.x, dim = g.dim;
+    const int bi = blockIdx.x;
     const int64_t r = blockIdx.y;
-    // tile index -> (bi, bj), bi >= bj
-    int bi = 0, t = blockIdx.x;
-    while (t > bi) { t -= bi + 1; bi++; }
-    const int bj = t;
     const double* kinv = g.kinv + r * (int64_t)g.n_pad * g.n_pad;
     const double* al = g.alpha + r * (int64_t)g.n_pad;
-    for (int e = tid; e < 64 * dim; e += 256) {
-        const int p = e / dim, k = e % dim;
-        xi[k][p] = g.x_pad[(int64_t)(bi * 64 + p) * dim + k];
-        xj[k][p] = g.x_pad[(int64_t)(bj * 64 + p) * dim + k];
+    for (int e = tid; e < 64 * DIMP; e += 256) {
+        const int p = e / DIMP, k = e % DIMP;
+        xi[k][p] = k < dim ? g.x_pad[(int64_t)(bi * 64 + p) * dim + k] : 0.0;
     }
-    if (tid < 64) { ai[tid] = al[bi * 64 + tid]; aj[tid] = al[bj * 64 + tid]; }
-    if (tid < dim) il[tid] = g.inv_ell2[r * dim + tid];
-    __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[BOGP_MAX_DIM];
+    if (tid < 64) { ai[tid] = al[bi * 64 + tid]; etab[tid] = kExp2Tab[tid]; }
+    if (tid < DIMP) ils[tid] = tid < dim ? g.inv_ell2[r * dim + tid] : 0.0;
+    // thread = 8 rows (its warp's) x 2 adjacent columns (its lane's): K^-1 is read as one double2 per row and thread
+    // (a warp reads 512 contiguous bytes), column coordinates as conflict-free double2, row coordinates as broadcasts
+    const int lane = tid & 31, wrp = tid >> 5;
+    double acc[DIMP];
 #pragma unroll
-    for (int k = 0; k < BOGP_MAX_DIM; k++) acc[k] = 0.0;
+    for (int k = 0; k < DIMP; k++) acc[k] = 0.0;
+    for (int bj = 0; bj <= bi; bj++) {
+        __syncthreads();                                   // the previous tile is done with xj / aj
+        for (int e = tid; e < 64 * DIMP; e += 256) {
+            const int p = e / DIMP, k = e % DIMP;
+            xj[k][p] = k < dim ? g.x_pad[(int64_t)(bj * 64 + p) * dim + k] : 0.0;
+        }
+        if (tid < 64) aj[tid] = al[bj * 64 + tid];
+        __syncthreads();
+        double xj0[DIMP], xj1[DIMP];
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int li = ty * 4 + a, i = bi * 64 + li;
-        const double2 k01 = *reinterpret_cast<const double2*>(kinv + (int64_t)i * g.n_pad + bj * 64 + tx * 4);
-        const double2 k23 = *reinterpret_cast<const double2*>(kinv + (int64_t)i * g.n_pad + bj * 64 + tx * 4 + 2);
-        const double kv[4] = {k01.x, k01.y, k23.x, k23.y};
+        for (int k = 0; k < DIMP; k++) {
+            const double2 v = *reinterpret_cast<const double2*>(&xj[k][2 * lane]);
+            xj0[k] = v.x; xj1[k] = v.y;
+        }
+        const double2 ajv = *reinterpret_cast<const double2*>(&aj[2 * lane]);
+        const int j0 = bj * 64 + 2 * lane;
+#pragma unroll 2
+        for (int a = 0; a < 8; a++) {
+            const int li = wrp * 8 + a, i = bi * 64 + li;
+            if (i >= g.n || j0 >= i) continue;                     // rows of real points; columns strictly left of the diagonal
+            const double2 kv = *reinterpret_cast<const double2*>(kinv + (int64_t)i * g.n_pad + j0);
+            const double aiv = ai[li];
+            {
+                double s = 0.0, d2[DIMP];
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int lj = tx * 4 + b, j = bj * 64 + lj;
-            if (j >= i || i >= g.n) continue;                  // strictly lower pairs of real points
-            double s = 0.0, d2[BOGP_MAX_DIM];
+                for (int k = 0; k < DIMP; k++) { const double df = xi[k][li] - xj0[k]; d2[k] = df * df; s += d2[k] * ils[k]; }
+                const double c = (aiv * ajv.x - kv.x) * exp_nonpos(-0.5 * s, etab);
 #pragma unroll
-            for (int k = 0; k < BOGP_MAX_DIM; k++)
-                if (k < dim) { const double df = xi[k][li] - xj[k][lj]; d2[k] = df * df; s += d2[k] * il[k]; }
-            const double c = (ai[li] * aj[lj] - kv[b]) * exp_nonpos(-0.5 * s);
+                for (int k = 0; k < DIMP; k++) acc[k] += c * d2[k];
+            }
+            if (j0 + 1 < i) {
+                double s = 0.0, d2[DIMP];
 #pragma unroll
-            for (int k = 0; k < BOGP_MAX_DIM; k++) if (k < dim) acc[k] += c * d2[k];
+                for (int k = 0; k < DIMP; k++) { const double df = xi[k][li] - xj1[k]; d2[k] = df * df; s += d2[k] * ils[k]; }
+                const double c = (aiv * ajv.y - kv.y) * exp_nonpos(-0.5 * s, etab);
+#pragma unroll
+                for (int k = 0; k < DIMP; k++) acc[k] += c * d2[k];
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < BOGP_MAX_DIM; k++) {
-        if (k < dim) {                                         // fixed xor tree over the warp, then the 8 warps in order
-            double v = acc[k];
+    for (int k = 0; k < DIMP; k++) {                               // fixed xor tree over the warp, then the 8 warps in order
+        double v = acc[k];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0) red[tid >> 5][k] = v;
-        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[tid >> 5][k] = v;
     }
     __syncthreads();
     if (tid < dim) {
         double s = 0.0;
 #pragma unroll
         for (int q = 0; q < 8; q++) s += red[q][tid];
-        g.gpart[(r * g.ntiles + blockIdx.x) * dim + tid] = s;
+        g.gpart[(r * g.nrb + bi) * dim + tid] = s;
     }
 }
 
@@ -299,13 +317,18 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
             k.A = Wb; k.lda = np; k.strideA = mat; k.B = Wb; k.ldb = np; k.strideB = mat; k.C = Ab; k.ldc = np; k.strideC = mat;
             k.M = (int)np; k.N = (int)np; k.K = (int)np; k.alpha = 1.0; k.accumulate = 0; k.lower_only = 1;
             rc = launch_gemm<128, 128, A_KM, B_KN, K_GE_MAXMN>(ctx, k, rb); if (rc) return rc;
-            const int nt = (int)(np / 64), ntiles = nt * (nt + 1) / 2;
-            GradArgs ga{x_pad, il + r0 * dim, alpha + r0 * np, Ab, gpart + r0 * ntiles * dim, (int)n, (int)np, dim, ntiles};
-            grad_contract_kernel<<<dim3(ntiles, rb), 256, 0, st>>>(ga); BOGP_LAUNCH_CHECK(ctx);
+            const int nt = (int)(np / 64);
+            GradArgs ga{x_pad, il + r0 * dim, alpha + r0 * np, Ab, gpart + r0 * nt * dim, (int)n, (int)np, dim, nt};
+            const dim3 ggrid(nt, rb);
+#define BOGP_GRAD(D) grad_contract_kernel<D><<<ggrid, 256, 0, st>>>(ga)
+            if (dim <= 2) BOGP_GRAD(2); else if (dim <= 4) BOGP_GRAD(4); else if (dim <= 6) BOGP_GRAD(6); else if (dim <= 8) BOGP_GRAD(8);
+            else if (dim <= 10) BOGP_GRAD(10); else if (dim <= 12) BOGP_GRAD(12); else BOGP_GRAD(16);
+#undef BOGP_GRAD
+            BOGP_LAUNCH_CHECK(ctx);
         }
     }
     lml_finish_kernel<<<(unsigned)((r + 7) / 8), 256, 0, st>>>(y_pad, alpha, logdet, gpart, d_ell, d_nlml_out, d_grad_out,
-                                                             (int)n, (int)np, dim, (int)((np / 64) * (np / 64 + 1) / 2), r);
+                                                             (int)n, (int)np, dim, (int)(np / 64), r);
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }
