@@ -284,6 +284,16 @@ class GPEngine:
         if de.ndim != 2 or de.shape[1] != dim:
             raise ValueError("ells must be (R, d)")
         r = de.shape[0]
+        if r == 1 and n > 256 and not want_grad:
+            # one large system: the pipelined single-matrix factorisation (bogp_fit_create) is faster than the batched
+            # driver; same kernels, same nlml.  A non-positive-definite matrix gives NaN like the batched path.
+            try:
+                f = self.fit(dx, dy, de[0] if isinstance(ells, torch.Tensor) else np.asarray(ells, dtype=np.float64)[0], jitter)
+            except np.linalg.LinAlgError:
+                return torch.full((1,), float("nan"), dtype=torch.float64, device=self.device)
+            val = f.nlml
+            f.close()
+            return torch.tensor([val], dtype=torch.float64, device=self.device)
         out = torch.empty(r, dtype=torch.float64, device=self.device)
         grad = torch.empty((r, dim), dtype=torch.float64, device=self.device) if want_grad else None
         need = self.lib.bogp_nlml_batched_workspace_bytes(n, dim, r, 1 if want_grad else 0)
