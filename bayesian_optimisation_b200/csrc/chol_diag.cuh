@@ -38,6 +38,13 @@ struct DiagSmem {
     double dg[kDiagNB];
 };
 
+#ifdef BOGP_DIAG_TRACE
+__device__ long long g_diag_trace[64];
+#define BOGP_DIAG_STAMP(k) do { if (threadIdx.x == 0) g_diag_trace[k] = clock64(); } while (0)
+#else
+#define BOGP_DIAG_STAMP(k) do {} while (0)
+#endif
+
 __device__ __forceinline__ double rcp_newton(double x) {   // hardware seed + 2 Newton steps (~1 ulp)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -73,6 +80,7 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
     const unsigned half_mask = 0xFFFFu << (lane & 16);
     for (int jb = 0; jb < NB / 4; jb++) {
         const int j0 = 4 * jb, buf = jb & 1;
+        BOGP_DIAG_STAMP(3 * jb);
         if (tx == jb) {                                       // the half-warp that owns columns j0..j0+3 (all 16 lanes)
             const int dl = (lane & 16) + jb;                  // lane of the diagonal thread (ty == jb)
             double up[4][4], cp[4][4];
@@ -115,6 +123,7 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
             }
         }
         __syncthreads();
+        BOGP_DIAG_STAMP(3 * jb + 1);
         if (active && 4 * ty + 3 > j0) {
             double c[4][4];                                   // c[p][i] = colC_p[row i]
 #pragma unroll
@@ -159,8 +168,10 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
                 }
             }
         }
+        BOGP_DIAG_STAMP(3 * jb + 2);
     }
     __syncthreads();
+    BOGP_DIAG_STAMP(48);
     double (&isd_s)[NB] = sm.colU[0][0];
     double (&d_s)[NB] = sm.colU[0][1];
     if (tid < NB) {                                           // isd_j = 1/sqrt(a_jj), d_j = a_jj * isd_j
@@ -192,6 +203,7 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (tid == 0) g.logdet[mat] += s;
     }
+    BOGP_DIAG_STAMP(49);
 }
 
 __global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {

@@ -34,6 +34,9 @@ int main() {
             for (int k = j; k <= i; k++) t += l[i * n + k] * x[k * n + j];
             err = fmax(err, fabs(s - h[i * n + j])); errx = fmax(errx, fabs(t - (i == j)));
         }
+#ifdef BOGP_DIAG_TRACE
+        if (variant == 2) { long long tr[64]; cudaMemcpyFromSymbol(tr, g_diag_trace, sizeof(tr)); printf("groups (panel+barrier | update) cycles:"); for (int jb = 0; jb < 16; jb++) printf(" %lld|%lld", tr[3*jb+1]-tr[3*jb], tr[3*jb+2]-tr[3*jb+1]); printf("\n total loop %lld, epilogue %lld cycles\n", tr[48]-tr[0], tr[49]-tr[48]); }
+#endif
         printf("variant %d: %.2f us   |LL^T-A| %.2e  |L X - I| %.2e  (%s)\n", variant, best * 1e3, err, errx, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
