@@ -255,9 +255,32 @@ def run_gpu_arm(args):
     ms = float(t.item())
     value = world * cands * args.steps / (ms * 1e-3)
 
-    # ---- fit time alone (CUDA events, best of 3)
+    # ---- the reference's own acquisition (explore*sigma - mu, "LCB/UCB", point_selector.py:204) on the same slices:
+    #      same sweep, different epilogue; reported beside the EI headline
+    def lcb_step(k):
+        fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
+        b, e = step_range(k)
+        res = eng.acquire(fit, grid, b, e, kind=0, explore=4.0, chunk=args.chunk)
+        out = allreduce_maxloc(res.best_score, res.best_index, device=dev) if world > 1 else (res.best_score, res.best_index)
+        fit.close()
+        return out
+    lcb_step(0)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for k in range(2):
+        lcb_step(1 + k)
+    a1.record()
+    barrier()
+    tl = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    lcb_value = world * cands * 2 / (float(tl.item()) * 1e-3)
+
+    # ---- fit time alone (CUDA events, best of 10: the fit is latency-bound, so it follows the SM clock, which stays
+    #      power-capped for a while after the sweeps above)
     fit_ms = 1e30
-    for _ in range(3):
+    for _ in range(10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); f = eng.fit(dX, dy, ell, JITTER_POSTERIOR); b.record(); torch.cuda.synchronize()
         fit_ms = min(fit_ms, a.elapsed_time(b)); f.close()
@@ -338,6 +361,8 @@ def run_gpu_arm(args):
                     "ms_per_launch": per_launch_ms, "launches_timed": tri_n, "executed_int8_ops_per_launch": int8_ops,
                     "algorithmic_flops_per_launch": flops, "fp64_equivalent_tflops": fp64_equiv,
                     "fp64_pipe_peak_tflops": max(fp64_peak, 37.0), "frac_of_fp64_pipe_peak": fp64_equiv / max(fp64_peak, 37.0),
+                    "frac_of_nominal_int8_peak": achieved / 4500.0,
+                    "ncu_utcimma_int8_pct_of_peak": (json.load(open(tj)).get("i8", {}).get("utcimma_int8_ops_pct_of_peak") if os.path.isfile(tj) else None),
                     "peak_source": ("dense int8 tensor peak taken as 2 x the measured cuBLAS bf16 burst figure of MEASURED_PEAKS.json "
                                     f"({bf16} TF/s; int8 runs at twice the bf16 rate, nominal 4500 vs 2250) -- of measured"
                                     if bf16 else "2 x the fallback bf16 figure 1590 TF/s -- of fallback"),
@@ -362,6 +387,7 @@ def run_gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": dict(workload_config(cands, world), tensor_path=eng.acquire_path), "fit_ms": fit_ms,
+                "lcb_candidates_per_s": lcb_value,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "PointSelector.update_surrogate() + expected_improvement() with host numpy buffers", "candidates_per_step_per_gpu": e2e_cands,
                         "steps": e2e_steps},
