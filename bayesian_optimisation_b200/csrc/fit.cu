@@ -434,13 +434,13 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
             GemmArgs t{};
             t.A = P1; t.lda = lda; t.B = Wdd; t.ldb = ldw; t.C = Tp; t.ldc = w;
             t.M = (int)r1; t.N = (int)w; t.K = (int)w; t.alpha = 1.0;
-            if ((rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, t, 1))) return rc;
+            if ((rc = launch_gemm<32, 32, A_MK, B_NK, K_ALL>(ctx, t, 1))) return rc;
             BOGP_CUDA_CHECK(cudaEventRecord(e_t1, cs));
             if (ko > 0) BOGP_CUDA_CHECK(cudaStreamWaitEvent(cs, e_rest, 0));    // A[R1, R1] received the previous panel's bulk update
             GemmArgs s{};
             s.A = Tp; s.lda = w; s.B = Tp; s.ldb = w; s.C = d_a + row1 * (lda + 1); s.ldc = lda;
             s.M = (int)r1; s.N = (int)r1; s.K = (int)w; s.alpha = -1.0; s.accumulate = 1; s.lower_only = 1;
-            if ((rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, s, 1))) return rc;
+            if ((rc = launch_gemm<32, 32, A_MK, B_NK, K_ALL>(ctx, s, 1))) return rc;
         }
         {   // ---- bulk, on the caller's stream
             BOGP_CUDA_CHECK(cudaStreamWaitEvent(bs, e_t1, 0));
