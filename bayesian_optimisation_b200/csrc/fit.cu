@@ -460,7 +460,7 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
                 GemmArgs d{};       // A[R2, R1 columns] -= P2 P1^T
                 d.A = P2; d.lda = lda; d.B = P1; d.ldb = lda; d.C = d_a + (row1 + r1) * lda + row1; d.ldc = lda;
                 d.M = (int)r2; d.N = (int)r1; d.K = (int)w; d.alpha = -1.0; d.accumulate = 1;
-                if (r2 * r1 <= (int64_t)128 * 128 * 148) rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, d, 1);
+                if (r2 * r1 <= (int64_t)128 * 128 * 148) rc = launch_gemm<32, 64, A_MK, B_NK, K_ALL>(ctx, d, 1);
                 else {
                     rc = launch_gemm_tma_nt(ctx, d);
                     if (rc == 1) rc = launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, d, 1);
