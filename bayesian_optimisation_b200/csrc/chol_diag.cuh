@@ -211,6 +211,13 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(DiagArgs g) {
     chol_diag_block(g, (int)blockIdx.x, sm);
 }
 
+// Batched variant (one CTA per matrix, hundreds of matrices): the kernel is latency-bound, so two CTAs per SM
+// nearly double the throughput; 128 registers per thread instead of 138.
+__global__ void __launch_bounds__(256, 2) chol_diag_batched_kernel(DiagArgs g) {
+    __shared__ __align__(16) DiagSmem sm;
+    chol_diag_block(g, (int)blockIdx.x, sm);
+}
+
 #ifdef BOGP_DIAG_BENCH
 struct DiagSmemV2 {
     double col[2][kDiagNB];    // u_i = a[i][j] before scaling (rows > j)

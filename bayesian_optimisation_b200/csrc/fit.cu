@@ -137,7 +137,8 @@ static int cholesky_blocked_v1(bogp_ctx* ctx, double* d_a, int64_t n, int64_t ld
         for (int64_t ki = 0; ki < wpan; ki += kDiagNB) {
             const int64_t k = ko + ki;
             DiagArgs dg{d_a, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, (int)(k / kDiagNB)};
-            BOGP_PROFILED(ctx, 4, (chol_diag_kernel<<<batch, 256, 0, ctx->stream>>>(dg)));
+            if (batch >= 2 * ctx->sm_count) { BOGP_PROFILED(ctx, 4, (chol_diag_batched_kernel<<<batch, 256, 0, ctx->stream>>>(dg))); }
+            else { BOGP_PROFILED(ctx, 4, (chol_diag_kernel<<<batch, 256, 0, ctx->stream>>>(dg))); }
             BOGP_LAUNCH_CHECK(ctx);
             const int below = (int)(n - (k + kDiagNB));
             if (below <= 0) break;
@@ -530,7 +531,8 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
         for (int64_t ki = 0; ki < wpan; ki += kDiagNB) {
             const int64_t k = ko + ki;
             DiagArgs dg{d_a, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, (int)(k / kDiagNB)};
-            BOGP_PROFILED(ctx, 4, (chol_diag_kernel<<<batch, 256, 0, ctx->stream>>>(dg)));
+            if (batch >= 2 * ctx->sm_count) { BOGP_PROFILED(ctx, 4, (chol_diag_batched_kernel<<<batch, 256, 0, ctx->stream>>>(dg))); }
+            else { BOGP_PROFILED(ctx, 4, (chol_diag_kernel<<<batch, 256, 0, ctx->stream>>>(dg))); }
             BOGP_LAUNCH_CHECK(ctx);
             const int below = (int)(wpan - (ki + kDiagNB));          // rows of the block under this step
             if (below <= 0) break;
