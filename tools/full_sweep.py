@@ -1,0 +1,51 @@
+"""BASELINE.json configs[2] in full: GP fit at N=4096, d=8 and an expected-improvement sweep over ALL 10^8 grid
+candidates, sharded over the ranks of the job (contiguous flat-index ranges, replicated fit, one 16-byte all_gather).
+
+    python tools/full_sweep.py                                   # 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 tools/full_sweep.py
+
+Prints one JSON line: wall and device time of fit + sweep + reduction, candidates/s, the selected flat index and its
+grid coordinates.  The index must be the same for every GPU count (fixed accumulation orders, exact integer product)."""
+import json, os, sys, time
+import numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import bench
+from bayesian_optimisation_b200.engine import GPEngine, CandidateGrid, JITTER_POSTERIOR, ACQ_EI
+from bayesian_optimisation_b200.sharding import allreduce_maxloc, shard_range
+
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+eng = GPEngine(local)
+X, y, ell = bench.synthetic()
+grid = CandidateGrid([np.linspace(0.0, 1.0, bench.GRID_PTS)] * bench.DIM)
+dX, dy = eng.to_device(X), eng.to_device(y)
+f_best = float(y.min())
+b, e = shard_range(grid.size, rank, world)
+# warm-up (kernel attributes, workspaces) on a small slice
+fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR); eng.acquire(fit, grid, b, b + 131072, kind=ACQ_EI, f_best=f_best); fit.close()
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter(); e0.record()
+fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
+res = eng.acquire(fit, grid, b, e, kind=ACQ_EI, f_best=f_best)
+score, index = allreduce_maxloc(res.best_score, res.best_index, device=dev) if world > 1 else (res.best_score, res.best_index)
+e1.record(); torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if rank == 0:
+    coords = np.unravel_index(index, grid.shape)
+    print(json.dumps({"config": "N=4096, d=8, EI over the full 10^8-point grid", "n_gpus": world, "candidates": grid.size,
+                      "device_seconds_max_over_ranks": float(ms.item()) * 1e-3, "wall_seconds_rank0": wall,
+                      "candidates_per_s": grid.size / (float(ms.item()) * 1e-3), "best_score": score, "best_flat_index": int(index),
+                      "best_grid_index": [int(c) for c in coords], "nlml": fit.nlml, "tensor_path": eng.acquire_path}))
+fit.close()
+if world > 1:
+    dist.destroy_process_group()
