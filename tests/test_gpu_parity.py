@@ -74,6 +74,38 @@ def test_kernel_matrix_odd_shapes(eng):
         np.testing.assert_allclose(K, o.kernel_rbf_chunked(A, B, ell), rtol=1e-13, atol=1e-300)
 
 
+def test_kernel_function_extremes(eng):
+    """exp_nonpos at its edges: coincident points give exactly 1 (+ jitter), huge scaled distances exactly 0
+    (results below 2^-1022 are flushed, numpy may return a denormal there), a NaN coordinate gives NaN."""
+    A = np.array([[0.0, 0.0], [1.0, 1.0], [0.5, 0.25]])
+    K = eng.kernel_matrix(A, A, np.array([0.01, 0.01]), 1e-4).cpu().numpy()
+    assert K[0, 0] == 1.0 + 1e-4 and K[1, 1] == 1.0 + 1e-4
+    assert K[0, 1] == 0.0 and K[1, 0] == 0.0
+    ref = o.kernel_rbf_chunked(A, A, np.array([0.01, 0.01]))
+    np.testing.assert_allclose(K - 1e-4 * np.eye(3), ref, rtol=1e-13, atol=1e-300)
+    # moderate arguments over the whole useful range: within 2 ulp of numpy
+    rng = np.random.default_rng(11)
+    P, Q = rng.random((300, 1)) * 37.0, np.zeros((1, 1))
+    got = eng.kernel_matrix(P, Q, np.array([1.0])).cpu().numpy()[:, 0]
+    want = np.exp(-0.5 * P[:, 0] ** 2)
+    assert np.all(np.abs(got - want) <= 2.0 * np.spacing(want))
+    B = A.copy(); B[2, 0] = np.nan
+    Kn = eng.kernel_matrix(B, A, np.array([0.3, 0.3])).cpu().numpy()
+    assert np.isnan(Kn[2]).all() and not np.isnan(Kn[:2]).any()
+
+
+def test_single_large_lml_uses_the_pipelined_fit_and_matches_oracle(eng):
+    n, d = 2100, 5
+    X, y, _ = o.synthetic_problem(n, d, seed=3)
+    ells = np.array([[0.35, 0.4, 0.3, 0.45, 0.5]])
+    got = eng.nlml_batched(X, y, ells).cpu().numpy()
+    ref = o.nlml(X, y, ells[0], stable=True)
+    assert abs(got[0] - ref) <= RTOL * abs(ref)
+    both = eng.nlml_batched(X, y, np.repeat(ells, 2, axis=0)).cpu().numpy()     # batched driver on the same system
+    np.testing.assert_allclose(both, [ref, ref], rtol=RTOL)
+    assert both[0] == both[1]
+
+
 # ------------------------------------------------------------------ K2 / fit
 @pytest.mark.parametrize("n,d", [(64, 3), (256, 4), (1024, 6)])
 def test_cholesky_matches_numpy(eng, n, d):
@@ -100,7 +132,9 @@ def test_cholesky_reports_non_positive_definite(eng):
         eng.fit(X, np.ones(3), np.ones(2), jitter=-2.0)
 
 
-@pytest.mark.parametrize("n,d", [(5, 2), (200, 3), (300, 4), (1024, 6), (1300, 5)])
+# 1024 / 1300 / 2100 / 4500: interleaved right-looking triangular inverse with 4 / 6 / 9 / 18 panels (the last one
+# beyond 4096 rows with a panel count that is not a power of two, so not the recursive-doubling schedule)
+@pytest.mark.parametrize("n,d", [(5, 2), (200, 3), (300, 4), (1024, 6), (1300, 5), (2100, 4), (4500, 6)])
 def test_fit_state_matches_numpy(eng, n, d):
     e = _consts()
     X, y, ell = o.synthetic_problem(n, d, seed=7 + n)
