@@ -31,6 +31,8 @@ struct DiagArgs {
 #define BOGP_DIAG_GROUPS (kDiagNB / 4)
 #endif
 struct DiagSmem {
+    // column buffers: the value of row 4t + 2h + e sits at [32 h + 2 t + e], so that the 16 threads of a half-warp read and
+    // write consecutive 16-byte pieces (conflict-free 128-bit accesses)
     double colU[2][4][kDiagNB];   // u_p[i] = A[i][j0+p] after the in-group updates (rows > j0+p, else 0)
     double colC[2][4][kDiagNB];   // u_p[i] / a_pp
     double rows[2][4][kDiagNB];   // R[j0+p][c] as it was when the group started
@@ -40,9 +42,12 @@ struct DiagSmem {
 
 #ifdef BOGP_DIAG_TRACE
 __device__ long long g_diag_trace[64];
+__device__ long long g_diag_trace2[16][8];
+#define BOGP_DIAG_STAMP2(cond, g, k) do { if (cond) g_diag_trace2[g][k] = clock64(); } while (0)
 #define BOGP_DIAG_STAMP(k) do { if (threadIdx.x == 0) g_diag_trace[k] = clock64(); } while (0)
 #else
 #define BOGP_DIAG_STAMP(k) do {} while (0)
+#define BOGP_DIAG_STAMP2(cond, g, k) do {} while (0)
 #endif
 
 __device__ __forceinline__ double rcp_newton(double x) {   // hardware seed + 2 Newton steps (~1 ulp)
@@ -83,6 +88,7 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
         BOGP_DIAG_STAMP(3 * jb);
         if (tx == jb) {                                       // the half-warp that owns columns j0..j0+3 (all 16 lanes)
             const int dl = (lane & 16) + jb;                  // lane of the diagonal thread (ty == jb)
+            BOGP_DIAG_STAMP2(ty == jb, jb, 0);
             double up[4][4], cp[4][4];
 #pragma unroll
             for (int p = 0; p < 4; p++) {
@@ -101,12 +107,13 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
                 }
                 if (ty == jb) sm.dg[j0 + p] = app;
             }
+            BOGP_DIAG_STAMP2(ty == jb, jb, 1);
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                *reinterpret_cast<double2*>(&sm.colU[buf][p][4 * ty])     = make_double2(up[p][0], up[p][1]);
-                *reinterpret_cast<double2*>(&sm.colU[buf][p][4 * ty + 2]) = make_double2(up[p][2], up[p][3]);
-                *reinterpret_cast<double2*>(&sm.colC[buf][p][4 * ty])     = make_double2(cp[p][0], cp[p][1]);
-                *reinterpret_cast<double2*>(&sm.colC[buf][p][4 * ty + 2]) = make_double2(cp[p][2], cp[p][3]);
+                *reinterpret_cast<double2*>(&sm.colU[buf][p][2 * ty])      = make_double2(up[p][0], up[p][1]);
+                *reinterpret_cast<double2*>(&sm.colU[buf][p][32 + 2 * ty]) = make_double2(up[p][2], up[p][3]);
+                *reinterpret_cast<double2*>(&sm.colC[buf][p][2 * ty])      = make_double2(cp[p][0], cp[p][1]);
+                *reinterpret_cast<double2*>(&sm.colC[buf][p][32 + 2 * ty]) = make_double2(cp[p][2], cp[p][3]);
             }
             if (ty == jb) {
 #pragma unroll
@@ -122,21 +129,23 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
                 *reinterpret_cast<double2*>(&sm.rows[buf][p][4 * tx + 2]) = make_double2(r[p][2], r[p][3]);
             }
         }
+        BOGP_DIAG_STAMP2(tx == jb && ty == jb, jb, 2);
         __syncthreads();
+        BOGP_DIAG_STAMP2(tx == jb + 1 && ty == jb + 1, jb, 3);
         BOGP_DIAG_STAMP(3 * jb + 1);
         if (active && 4 * ty + 3 > j0) {
             double c[4][4];                                   // c[p][i] = colC_p[row i]
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                const double2 c01 = *reinterpret_cast<const double2*>(&sm.colC[buf][p][4 * ty]);
-                const double2 c23 = *reinterpret_cast<const double2*>(&sm.colC[buf][p][4 * ty + 2]);
+                const double2 c01 = *reinterpret_cast<const double2*>(&sm.colC[buf][p][2 * ty]);
+                const double2 c23 = *reinterpret_cast<const double2*>(&sm.colC[buf][p][32 + 2 * ty]);
                 c[p][0] = c01.x; c[p][1] = c01.y; c[p][2] = c23.x; c[p][3] = c23.y;
             }
             if (tx > jb) {                                    // trailing columns (the group's own columns were updated by their owners)
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
-                    const double2 k01 = *reinterpret_cast<const double2*>(&sm.colU[buf][p][4 * tx]);
-                    const double2 k23 = *reinterpret_cast<const double2*>(&sm.colU[buf][p][4 * tx + 2]);
+                    const double2 k01 = *reinterpret_cast<const double2*>(&sm.colU[buf][p][2 * tx]);
+                    const double2 k23 = *reinterpret_cast<const double2*>(&sm.colU[buf][p][32 + 2 * tx]);
                     const double cc[4] = {k01.x, k01.y, k23.x, k23.y};
 #pragma unroll
                     for (int cidx = 0; cidx < 4; cidx++)
@@ -144,7 +153,11 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
                         for (int i = 0; i < 4; i++) a[i][cidx] -= c[p][i] * cc[cidx];
                 }
             }
+#ifdef BOGP_DIAG_NO_INVERSE
+            if (false) {
+#else
             if (tx <= jb) {                                   // inverse: fold the in-group dependencies into the coefficients
+#endif
                 double m[4][4];
 #pragma unroll
                 for (int p = 1; p < 4; p++)
@@ -168,6 +181,8 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
                 }
             }
         }
+        BOGP_DIAG_STAMP2(tx == jb + 1 && ty == jb + 1, jb, 4);
+        BOGP_DIAG_STAMP2(tx == jb && ty == jb, jb, 5);
         BOGP_DIAG_STAMP(3 * jb + 2);
     }
     __syncthreads();
@@ -186,22 +201,46 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
     }
     __syncthreads();
     double* W = g.w ? g.w + mat * g.strideW + (int64_t)g.kblk * NB * (g.ldw + 1) : nullptr;
+    const bool vec = (((g.lda | g.ldw) & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+    const double2 isd01 = *reinterpret_cast<const double2*>(&isd_s[4 * tx]), isd23 = *reinterpret_cast<const double2*>(&isd_s[4 * tx + 2]);
+    const double isd_c[4] = {isd01.x, isd01.y, isd23.x, isd23.y};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int row = 4 * ty + i;
         const double isd_row = isd_s[row];
+        double la[4], lw[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int cc = 4 * tx + c;
-            if (active && cc <= row) A[(int64_t)row * g.lda + cc] = (cc == row) ? d_s[row] : a[i][c] * isd_s[cc];
-            if (W) W[(int64_t)row * g.ldw + cc] = (active && cc <= row) ? r[i][c] * isd_row : 0.0;
+            la[c] = (cc == row) ? d_s[row] : a[i][c] * isd_c[c];
+            lw[c] = (active && cc <= row) ? r[i][c] * isd_row : 0.0;
+        }
+        // a thread owns 4 consecutive columns of the row = one 32-byte sector: two 16-byte stores when aligned
+        double* arow = A + (int64_t)row * g.lda + 4 * tx;
+        if (ty > tx && vec) {                                 // entirely below the diagonal
+            *reinterpret_cast<double2*>(arow) = make_double2(la[0], la[1]);
+            *reinterpret_cast<double2*>(arow + 2) = make_double2(la[2], la[3]);
+        } else if (ty >= tx) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) if (4 * tx + c <= row) arow[c] = la[c];
+        }
+        if (W) {
+            double* wrow = W + (int64_t)row * g.ldw + 4 * tx;
+            if (vec) {
+                *reinterpret_cast<double2*>(wrow) = make_double2(lw[0], lw[1]);
+                *reinterpret_cast<double2*>(wrow + 2) = make_double2(lw[2], lw[3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) wrow[c] = lw[c];
+            }
         }
     }
     if (tid < 32 && g.logdet) {   // log det = sum log a_jj (= 2 sum log d_j), fixed order
         double s = log(sm.dg[tid]) + log(sm.dg[tid + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) g.logdet[mat] += s;
+        if (tid == 0) atomicAdd(g.logdet + mat, s);      // fire-and-forget (no read-modify-write round trip on the chain); one add per
+                                                          // diagonal block, issued in factorisation order, so the sum is still deterministic
     }
     BOGP_DIAG_STAMP(49);
 }
@@ -324,7 +363,8 @@ __device__ __forceinline__ void chol_diag_block_v2(const DiagArgs& g, int mat, D
         double s = log(dg[tid]) + log(dg[tid + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) g.logdet[mat] += s;
+        if (tid == 0) atomicAdd(g.logdet + mat, s);      // fire-and-forget (no read-modify-write round trip on the chain); one add per
+                                                          // diagonal block, issued in factorisation order, so the sum is still deterministic
     }
 }
 

@@ -35,7 +35,8 @@ int main() {
             err = fmax(err, fabs(s - h[i * n + j])); errx = fmax(errx, fabs(t - (i == j)));
         }
 #ifdef BOGP_DIAG_TRACE
-        if (variant == 2) { long long tr[64]; cudaMemcpyFromSymbol(tr, g_diag_trace, sizeof(tr)); printf("groups (panel+barrier | update) cycles:"); for (int jb = 0; jb < 16; jb++) printf(" %lld|%lld", tr[3*jb+1]-tr[3*jb], tr[3*jb+2]-tr[3*jb+1]); printf("\n total loop %lld, epilogue %lld cycles\n", tr[48]-tr[0], tr[49]-tr[48]); }
+        if (variant == 2) { long long tr[64]; cudaMemcpyFromSymbol(tr, g_diag_trace, sizeof(tr)); printf("groups (panel+barrier | update) cycles:"); for (int jb = 0; jb < 16; jb++) printf(" %lld|%lld", tr[3*jb+1]-tr[3*jb], tr[3*jb+2]-tr[3*jb+1]); printf("\n total loop %lld, epilogue %lld cycles\n", tr[48]-tr[0], tr[49]-tr[48]);
+          long long t2[16][8]; cudaMemcpyFromSymbol(t2, g_diag_trace2, sizeof(t2)); printf("per group: panel | publish | barrier->next owner | next owner trailing update | (owner inverse update)\n"); for (int jb = 1; jb < 15; jb++) printf("  g%2d: %5lld %5lld %5lld %5lld (%5lld)   start-to-start %lld\n", jb, t2[jb][1]-t2[jb][0], t2[jb][2]-t2[jb][1], t2[jb][3]-t2[jb][2], t2[jb][4]-t2[jb][3], t2[jb][5]-t2[jb][2], t2[jb+1][0]-t2[jb][0]); }
 #endif
         printf("variant %d: %.2f us   |LL^T-A| %.2e  |L X - I| %.2e  (%s)\n", variant, best * 1e3, err, errx, cudaGetErrorString(cudaGetLastError()));
     }
