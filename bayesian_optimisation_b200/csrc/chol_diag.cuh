@@ -74,14 +74,22 @@ __device__ __forceinline__ void chol_diag_block(const DiagArgs& g, int mat, Diag
     double* A = g.a + mat * g.strideA + (int64_t)g.kblk * NB * (g.lda + 1);
     const bool active = ty >= tx;
     double a[4][4], r[4][4];
+    const bool vec_in = ((g.lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 4; i++) {
+        const int row = 4 * ty + i;
+        const double* arow = A + (int64_t)row * g.lda + 4 * tx;
+        if (ty > tx && vec_in) {                              // one 32-byte sector per thread and row: two 16-byte loads
+            const double2 v01 = __ldcg(reinterpret_cast<const double2*>(arow));      // L2-coherent: other CTAs may have written it
+            const double2 v23 = __ldcg(reinterpret_cast<const double2*>(arow + 2));
+            a[i][0] = v01.x; a[i][1] = v01.y; a[i][2] = v23.x; a[i][3] = v23.y;
+        } else {
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int row = 4 * ty + i, cc = 4 * tx + c;
-            a[i][c] = (active && cc <= row) ? __ldcg(A + (int64_t)row * g.lda + cc) : 0.0;   // L2-coherent: other CTAs may have written it
-            r[i][c] = (row == cc) ? 1.0 : 0.0;
+            for (int c = 0; c < 4; c++) a[i][c] = (active && 4 * tx + c <= row) ? __ldcg(arow + c) : 0.0;
         }
+#pragma unroll
+        for (int c = 0; c < 4; c++) r[i][c] = (row == 4 * tx + c) ? 1.0 : 0.0;
+    }
     const unsigned half_mask = 0xFFFFu << (lane & 16);
     for (int jb = 0; jb < NB / 4; jb++) {
         const int j0 = 4 * jb, buf = jb & 1;
