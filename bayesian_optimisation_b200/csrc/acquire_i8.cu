@@ -130,17 +130,82 @@ __device__ __forceinline__ void transpose4x4_bytes(uint32_t w0, uint32_t w1, uin
 // (coordinate 0, 1/ell^2 = 0) and add exactly +0 to the squared distance.
 // k_*(x_j, p) for one row of the shared x block ([row][DIMP], read with 16-byte broadcast loads); same operation
 // order as every other kernel-function site (Gram, FP64 panel, LML): s += ((p_k - x_k)^2) / ell_k^2, k ascending.
-template <int DIMP>
-__device__ __forceinline__ double kstar_row(const double (&pc)[DIMP], const double (&il)[DIMP], const double* xrow, const double* etab) {
+// T = number of trailing dimensions summed here; the leading DIMP - T dimensions (coordinates shared by all candidates
+// of the tile) arrive as the partial sum `s` of the same operations in the same order, so the result is bit-identical
+// to T = DIMP with s = 0.
+template <int DIMP, int T>
+__device__ __forceinline__ double kstar_row(double s, const double (&pc)[DIMP], const double (&il)[DIMP], const double* xrow, const double* etab) {
+    constexpr int K0 = DIMP - T;
+    if (K0 & 1) { const double d = pc[K0] - xrow[K0]; s += (d * d) * il[K0]; }
+    constexpr int K1 = K0 + (K0 & 1);
     const double2* xr = reinterpret_cast<const double2*>(xrow);
-    double s = 0.0;
 #pragma unroll
-    for (int k2 = 0; k2 < DIMP / 2; k2++) {
+    for (int k2 = K1 / 2; k2 < DIMP / 2; k2++) {
         const double2 xv = xr[k2];
         const double d0 = pc[2 * k2] - xv.x;     s += (d0 * d0) * il[2 * k2];
         const double d1 = pc[2 * k2 + 1] - xv.y; s += (d1 * d1) * il[2 * k2 + 1];
     }
     return exp_nonpos(-0.5 * s, etab);
+}
+
+// the row groups of one panel tile for one thread (= one candidate): digits + partial posterior mean
+struct PanelRowCtx {
+    const double* xs; const double* al; const double* etab; const double* pre;     // shared memory
+    uint8_t* panel; int64_t tile_base;    // (ct * (n_pad / 32) + jb * 8) * kI8BTile
+    int nvr, jq, nl, tid; double jit;
+};
+
+template <int DIMP, bool UB, int T>
+__device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double (&pc)[DIMP], const double (&il)[DIMP]) {
+    double mu = 0.0;      // this thread's 4 row groups, ascending
+    // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
+    for (int g = c.tid >> 6; g < kAcqBM / 16; g += 4) {
+        uint32_t pk[kI8Slices][4];
+        double mug = 0.0;
+        if (UB) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; e4++) {
+                uint32_t lo[4], hi[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int jl = g * 16 + e4 * 4 + i;
+                    double v = kstar_row<DIMP, T>(T < DIMP ? c.pre[jl] : 0.0, pc, il, c.xs + jl * DIMP, c.etab);
+                    v = jl < c.nvr ? v : 0.0;
+                    if (jl == c.jq) v += c.jit;
+                    mug += c.al[jl] * v;
+                    const unsigned long long fx = __double2ull_rn(v * 18014398509481984.0);   // t = v / 2, fx = t * 2^55 = v * 2^54 (exact scaling)
+                    lo[i] = (uint32_t)fx; hi[i] = (uint32_t)(fx >> 32);
+                }
+                uint32_t tl[4], th[4];
+                transpose4x4_bytes(lo[0], lo[1], lo[2], lo[3], tl);      // digits 0..3 (least significant first)
+                transpose4x4_bytes(hi[0], hi[1], hi[2], hi[3], th);      // digits 4..6
+                pk[6][e4] = tl[0]; pk[5][e4] = tl[1]; pk[4][e4] = tl[2]; pk[3][e4] = tl[3];
+                pk[2][e4] = th[0]; pk[1][e4] = th[1]; pk[0][e4] = th[2];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kI8Slices; q++) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int jl = g * 16 + e;
+                double v = kstar_row<DIMP, T>(T < DIMP ? c.pre[jl] : 0.0, pc, il, c.xs + jl * DIMP, c.etab);
+                v = jl < c.nvr ? v : 0.0;
+                if (jl == c.jq) v += c.jit;
+                mug += c.al[jl] * v;
+                int d[kI8Slices];
+                balanced_digits(__double2ll_rn(v * 18014398509481984.0), d);   // t = v / 2, fx = t * 2^55 = v * 2^54
+#pragma unroll
+                for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
+            }
+        }
+        mu += mug;
+        // k tile (32 rows) = jb*8 + g/2, k chunk = g & 1
+        uint8_t* dst = c.panel + (c.tile_base + (g >> 1)) * kI8BTile + (g & 1) * (kI8Slices * kI8BN * 16) + c.nl * 16;
+#pragma unroll
+        for (int q = 0; q < kI8Slices; q++)
+            *reinterpret_cast<uint4*>(dst + q * (kI8BN * 16)) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+    }
+    return mu;
 }
 
 template <int DIMP, bool UB>
@@ -152,6 +217,8 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     __shared__ double sl[BOGP_MAX_DIM];
     __shared__ double etab[64];
     __shared__ double mured[4][kI8BN];
+    __shared__ double pre[kAcqBM];
+    __shared__ int kshare_s;
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
     const int ct = blockIdx.x, jb = blockIdx.y;
@@ -191,65 +258,48 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     }
     __syncthreads();
 
+    // Leading coordinates that ALL candidates of the tile share (a grid sweep: all but the last two or three axes):
+    // their part of the squared distance is computed once per row instead of once per entry.  Detected at run time on
+    // the staged candidate block, so explicit candidate arrays that happen to be grid-ordered benefit as well.
+    if (tid == 0) kshare_s = DIMP;
+    __syncthreads();
+    if (tid > 0 && tid < nvalid) {
+        int k = 0;
+        for (; k < dim; k++)
+            if (__double_as_longlong(ps_raw[tid * dim + k]) != __double_as_longlong(ps_raw[k])) break;
+        if (k < dim) atomicMin(&kshare_s, k);
+    }
+    __syncthreads();
+    const int trail = DIMP - kshare_s;             // dimensions that differ inside the tile (padding dimensions count as shared only when leading)
+    const int T = (DIMP > 4 && trail <= 2) ? 2 : ((DIMP > 4 && trail == 3) ? 3 : ((DIMP > 4 && trail == 4) ? 4 : DIMP));
+    if (T < DIMP) {                                // row prefixes over the first DIMP - T dimensions, candidate 0's coordinates
+        double s0 = 0.0;
+        for (int k = 0; k < DIMP - T; k++) {
+            const double d0 = (k < dim ? ps_raw[k] : 0.0) - xs[tid][k];
+            s0 += (d0 * d0) * sl[k];
+        }
+        pre[tid] = s0;
+    }
+    __syncthreads();
+
     const int nl = tid & 63;                       // candidate within the tile
     const int ncl = nl < nvalid ? nl : nvalid - 1;
     double pc[DIMP], il[DIMP];
 #pragma unroll
     for (int k = 0; k < DIMP; k++) { pc[k] = k < dim ? ps_raw[ncl * dim + k] : 0.0; il[k] = sl[k]; }
-    const int nvr = p.n - jb * kAcqBM;             // rows of this block that are real measurements (the rest is padding: k_* = 0)
+    PanelRowCtx rc;
+    rc.xs = &xs[0][0]; rc.al = al; rc.etab = etab; rc.pre = pre;
+    rc.panel = p.panel; rc.tile_base = (int64_t)ct * (p.n_pad / kI8KB) + (int64_t)jb * (kAcqBM / kI8KB);
+    rc.nvr = p.n - jb * kAcqBM;                    // rows of this block that are real measurements (the rest is padding: k_* = 0)
     // row of this block on which the reference's shape-equality jitter falls for this candidate (-1: none)
     const int64_t jq64 = (cbase + nl) - (int64_t)jb * kAcqBM;
-    const int jq = (p.cand.cross_jitter != 0.0 && jq64 >= 0 && jq64 < kAcqBM) ? (int)jq64 : -1;
-    const double jit = p.cand.cross_jitter;
-    double mu = 0.0;      // this thread's 4 row groups, ascending
-    // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
-    for (int g = tid >> 6; g < kAcqBM / 16; g += 4) {
-        uint32_t pk[kI8Slices][4];
-        double mug = 0.0;
-        if (UB) {
-#pragma unroll
-            for (int e4 = 0; e4 < 4; e4++) {
-                uint32_t lo[4], hi[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int jl = g * 16 + e4 * 4 + i;
-                    double v = kstar_row<DIMP>(pc, il, &xs[jl][0], etab);
-                    v = jl < nvr ? v : 0.0;
-                    if (jl == jq) v += jit;
-                    mug += al[jl] * v;
-                    const unsigned long long fx = __double2ull_rn(v * 18014398509481984.0);   // t = v / 2, fx = t * 2^55 = v * 2^54 (exact scaling)
-                    lo[i] = (uint32_t)fx; hi[i] = (uint32_t)(fx >> 32);
-                }
-                uint32_t tl[4], th[4];
-                transpose4x4_bytes(lo[0], lo[1], lo[2], lo[3], tl);      // digits 0..3 (least significant first)
-                transpose4x4_bytes(hi[0], hi[1], hi[2], hi[3], th);      // digits 4..6
-                pk[6][e4] = tl[0]; pk[5][e4] = tl[1]; pk[4][e4] = tl[2]; pk[3][e4] = tl[3];
-                pk[2][e4] = th[0]; pk[1][e4] = th[1]; pk[0][e4] = th[2];
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < kI8Slices; q++) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
-#pragma unroll
-            for (int e = 0; e < 16; e++) {
-                const int jl = g * 16 + e;
-                double v = kstar_row<DIMP>(pc, il, &xs[jl][0], etab);
-                v = jl < nvr ? v : 0.0;
-                if (jl == jq) v += jit;
-                mug += al[jl] * v;
-                int d[kI8Slices];
-                balanced_digits(__double2ll_rn(v * 18014398509481984.0), d);   // t = v / 2, fx = t * 2^55 = v * 2^54
-#pragma unroll
-                for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
-            }
-        }
-        mu += mug;
-        // k tile (32 rows) = jb*8 + g/2, k chunk = g & 1
-        uint8_t* dst = p.panel + ((int64_t)ct * (p.n_pad / kI8KB) + (int64_t)jb * (kAcqBM / kI8KB) + (g >> 1)) * kI8BTile
-                     + (g & 1) * (kI8Slices * kI8BN * 16) + nl * 16;
-#pragma unroll
-        for (int q = 0; q < kI8Slices; q++)
-            *reinterpret_cast<uint4*>(dst + q * (kI8BN * 16)) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
-    }
+    rc.jq = (p.cand.cross_jitter != 0.0 && jq64 >= 0 && jq64 < kAcqBM) ? (int)jq64 : -1;
+    rc.jit = p.cand.cross_jitter; rc.nl = nl; rc.tid = tid;
+    double mu;
+    if (DIMP > 4 && T == 2)      mu = panel_rows<DIMP, UB, (DIMP > 4 ? 2 : DIMP)>(rc, pc, il);
+    else if (DIMP > 4 && T == 3) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 3 : DIMP)>(rc, pc, il);
+    else if (DIMP > 4 && T == 4) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 4 : DIMP)>(rc, pc, il);
+    else                         mu = panel_rows<DIMP, UB, DIMP>(rc, pc, il);
     mured[tid >> 6][nl] = mu;
     __syncthreads();
     if (tid < kI8BN) {                              // fixed-order sum of the 4 thread groups

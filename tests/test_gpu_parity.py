@@ -231,6 +231,30 @@ def test_the_two_tensor_paths_agree(eng):
     assert out["i8"].best_index == out["fp64"].best_index
 
 
+@pytest.mark.parametrize("d,G", [(8, 4), (7, 4), (6, 5), (5, 6)])
+def test_shared_prefix_of_grid_ordered_candidates_changes_nothing(eng, d, G):
+    """The panel kernel computes the squared-distance part of coordinates shared by a whole 64-candidate tile once
+    per row (grid-ordered candidates share all but the last two to four axes).  Same operations, same order: every
+    candidate gets bit-identical mu and sigma whether the block is grid-ordered (shared prefix found) or randomly
+    permuted (no shared coordinates)."""
+    from bayesian_optimisation_b200.engine import CandidateGrid
+    e = _consts()
+    X, y, ell = o.synthetic_problem(700, d, seed=21 + d)
+    axes = [np.linspace(0, 1, G)] * d
+    P = o.candidate_grid(axes)[: 3 * 64 * 7 + 13]
+    perm = np.random.default_rng(d).permutation(len(P))
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    a = eng.acquire(fit, P, outputs=True)
+    b = eng.acquire(fit, np.ascontiguousarray(P[perm]), outputs=True)
+    c = eng.acquire(fit, CandidateGrid(axes), 0, len(P), outputs=True)
+    for name in ("mu", "sigma", "acq"):
+        ordered = getattr(a, name).cpu().numpy()
+        np.testing.assert_array_equal(getattr(b, name).cpu().numpy(), ordered[perm])
+        np.testing.assert_array_equal(getattr(c, name).cpu().numpy(), ordered)
+    assert perm[b.best_index] == a.best_index or a.acq.cpu().numpy()[perm[b.best_index]] == a.best_score
+    fit.close()
+
+
 def test_sharded_ranges_are_bit_identical_and_pick_the_same_index(eng):
     from bayesian_optimisation_b200.engine import CandidateGrid
     from bayesian_optimisation_b200.sharding import reduce_pairs, shard_range
