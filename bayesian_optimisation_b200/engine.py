@@ -119,6 +119,27 @@ class GPEngine:
             return a.to(device=self.device, dtype=dtype).contiguous()
         return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
 
+    def prefetch_to_device(self, a: np.ndarray):
+        """Start a host -> device copy on a side stream (asynchronous for pinned host memory) and return a handle for
+        `prefetched()`; work enqueued on the current stream meanwhile overlaps the copy."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        src = torch.from_numpy(a)
+        dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))     # dst may reuse memory still in use there
+        with torch.cuda.stream(self._copy_stream):
+            dst.copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        return dst, done, src
+
+    def prefetched(self, handle) -> torch.Tensor:
+        """The device tensor of a `prefetch_to_device` handle, ordered after its copy on the current stream."""
+        dst, done, _src = handle
+        torch.cuda.current_stream(self.device).wait_event(done)
+        dst.record_stream(torch.cuda.current_stream(self.device))
+        return dst
+
     def to_host(self, t: torch.Tensor) -> np.ndarray:
         """Device tensor -> numpy array through pinned host memory (torch's caching host allocator);
         the array owns its buffer, which returns to the cache when the array is collected."""

@@ -115,6 +115,12 @@ class PointSelector():
         self.measured_vals = np.array(self.measured_vals, dtype=np.float64)
         self._cov_pred = self._cov_meas = self._cov_meas_pred = None
 
+        # The candidate array starts its way to the device now, on a side stream: the copy (asynchronous when the caller's
+        # buffer is pinned) runs underneath the length-scale search and the fit below.
+        cand_dev = None
+        if self.predicted_axes is None:
+            cand_dev = self._eng().prefetch_to_device(np.ascontiguousarray(self.predicted_pts, dtype=np.float64))
+
         if len(self.measured_pts[:, 0]) > 1:
             self._log("Beginning ARD kernel tuning ...")
             self.tune_kernel()
@@ -134,8 +140,8 @@ class PointSelector():
                 cand = CandidateGrid([np.asarray(a, dtype=np.float64) for a in self.predicted_axes])
                 count, quirk = cand.size, False
             else:
-                cand = np.ascontiguousarray(self.predicted_pts, dtype=np.float64)
-                count, quirk = len(cand), cand.shape == self.measured_pts.shape   # jitter rule of :173-177 applied at :81
+                cand = eng.prefetched(cand_dev)
+                count, quirk = len(cand), tuple(cand.shape) == self.measured_pts.shape   # jitter rule of :173-177 applied at :81
             res = eng.acquire(fit, cand, 0, count, kind=ACQ_LCB, explore=4.0, prior_diag=PRIOR_DIAG, outputs=True,
                               cross_jitter=JITTER_LML if quirk else 0.0)
         finally:
