@@ -51,6 +51,10 @@ def test_library_contains_sm100a_tensor_and_tma_code(lib):
     assert "sm_100a" in sass
     assert "DMMA.8x8x4" in sass          # FP64 tensor path
     assert "UBLKCP" in sass              # bulk-TMA staging
+    assert "UTCIMMA" in sass             # tcgen05.mma kind::i8 (acquisition product)
+    assert "LDTM" in sass                # tcgen05.ld: TMEM accumulators read back in the epilogue
+    assert "UTMALDG" in sass             # tensor-map TMA loads (trailing SYRK)
+    assert "UCGABAR_ARV" in sass         # thread-block cluster barrier (in-block factorisation kernel)
 
 
 def test_workspace_queries_are_pure_host_functions(lib):
