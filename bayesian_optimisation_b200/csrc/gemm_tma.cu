@@ -5,17 +5,21 @@
 // K-contiguous operands are fetched by the TMA unit instead: a tensor map with a box of {4 k, 128 rows}
 // lands in shared memory as [row][4 doubles], which is exactly the DMMA.8x8x4 fragment order (a warp's
 // fragment = one contiguous 256-byte line, no padding, no bank conflicts).  One producer lane issues
-// 16 boxes per 32-wide k stage; 8 consumer warps (4 x 2, warp tile 32 x 64) do nothing but LDS + DMMA;
-// stages are handed over with mbarriers (no CTA-wide barrier in the main loop).
+// 16 boxes per 32-wide k stage; 4 consumer warps (warp tile 32 x 64, CTA tile 128 x 64) do nothing but LDS + DMMA;
+// stages are handed over with mbarriers (no CTA-wide barrier in the main loop); two CTAs share an SM.
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include <cuda.h>
 
 namespace bogp {
 
-constexpr int TBM = 128, TBN = 128, TKB = 32, TSTAGES = 3;
-constexpr int kTOperandBytes = TBM * TKB * 8;                 // 32 KB
-constexpr int kTStageBytes = 2 * kTOperandBytes;              // 64 KB
+// CTA tile 128 x 64 with FOUR consumer warps (32 x 64 each) and two stages, TWO CTAs per SM: while one CTA is in the
+// read-modify-write epilogue of its tile the other one keeps the DMMA pipe busy (with one 128 x 128 CTA per SM the
+// pipe idled through every epilogue: 65 % active).
+constexpr int TBM = 128, TBN = 64, TKB = 32, TSTAGES = 2, TCONSUMERS = 4;
+constexpr int kTABytes = TBM * TKB * 8;                       // 32 KB
+constexpr int kTBBytes = TBN * TKB * 8;                       // 16 KB
+constexpr int kTStageBytes = kTABytes + kTBBytes;             // 48 KB
 constexpr size_t kTSmem = (size_t)TSTAGES * kTStageBytes + 2 * TSTAGES * 8 + TSTAGES * 4 + 64;
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -37,7 +41,7 @@ struct TmaGemmArgs {
 // flight while the consumers are still in the read-modify-write epilogue of the current one.  Dynamic scheduling
 // matters because this kernel shares the GPU with the serial chain and the interleaved inverse: a CTA whose SM is
 // busy elsewhere simply takes fewer tiles.
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__((TCONSUMERS + 1) * 32, 2)
 gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaGemmArgs g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TSTAGES * kTStageBytes);
@@ -47,7 +51,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int nk = (g.K + TKB - 1) / TKB;
 
     if (tid == 0) {
-        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 8); }
+        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], TCONSUMERS); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -56,11 +60,11 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     auto tile_of = [&](int t, int& bm, int& bn) {
         if (!g.lower_only) { bm = t / g.nbn; bn = t - bm * g.nbn; return; }
         int r = 0;
-        for (; r < g.nbm; r++) { const int c = (r + 1 < g.nbn) ? r + 1 : g.nbn; if (t < c) break; t -= c; }
+        for (; r < g.nbm; r++) { const int c = ((r + 1) * (TBM / TBN) < g.nbn) ? (r + 1) * (TBM / TBN) : g.nbn; if (t < c) break; t -= c; }
         bm = r; bn = t;
     };
 
-    if (warp == 8) {
+    if (warp == TCONSUMERS) {
         if (lane == 0) {
             int it = 0;
             for (;;) {
@@ -79,7 +83,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                     for (int kk = 0; kk < TKB / 4; kk++) {
                         tma_load_2d(dst + kk * (TBM * 32), &mapA, kt * TKB + kk * 4, m0, &full[s]);
-                        tma_load_2d(dst + kTOperandBytes + kk * (TBN * 32), &mapB, kt * TKB + kk * 4, n0, &full[s]);
+                        tma_load_2d(dst + kTABytes + kk * (TBN * 32), &mapB, kt * TKB + kk * 4, n0, &full[s]);
                     }
                 }
             }
@@ -87,7 +91,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         return;
     }
 
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp, wn = 0;            // 4 consumer warps stacked along m: warp tile 32 x 64
     const int lr = lane >> 2, lk = lane & 3;
     int it = 0;
     for (;;) {
@@ -166,13 +170,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // rows x K row-major fp64 operand, leading dimension ld (doubles); box = {4 k, 128 rows}
-static bool make_operand_map(CUtensorMap* map, const double* base, int64_t rows, int64_t K, int64_t ld) {
+static bool make_operand_map(CUtensorMap* map, const double* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 2) != 0) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    const cuuint32_t box[2] = {4, 128};
+    const cuuint32_t box[2] = {4, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -183,22 +187,22 @@ static bool make_operand_map(CUtensorMap* map, const double* base, int64_t rows,
 int launch_gemm_tma_nt(bogp_ctx* ctx, const GemmArgs& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return BOGP_OK;
     alignas(64) CUtensorMap mapA, mapB;
-    if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb)) return 1;
+    if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda, TBM) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb, TBN)) return 1;
     static DeviceOnce configured;
     if (configured.need(ctx->device)) {
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmem));
     }
     const int nbm = (g.M + TBM - 1) / TBM, nbn = (g.N + TBN - 1) / TBN;
     int ntiles = nbm * nbn;
-    if (g.lower_only) { ntiles = 0; for (int r = 0; r < nbm; r++) ntiles += (r + 1 < nbn) ? r + 1 : nbn; }
+    if (g.lower_only) { ntiles = 0; for (int r = 0; r < nbm; r++) ntiles += ((r + 1) * (TBM / TBN) < nbn) ? (r + 1) * (TBM / TBN) : nbn; }
     // tile counters: a ring of 16 words, one per launch (launches on one stream are ordered; the ring keeps
     // launches that overlap on different streams apart)
     static int ring = 0;
     int* counter = ctx->d_flags + 32 + (ring++ & 15);
     BOGP_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
     TmaGemmArgs a{g.C, g.ldc, g.M, g.N, g.K, g.alpha, g.accumulate, g.lower_only, nbm, nbn, ntiles, counter};
-    const int ctas = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
-    gemm_tma_nt_kernel<<<ctas, 288, kTSmem, ctx->stream>>>(mapA, mapB, a);
+    const int ctas = ntiles < 2 * ctx->sm_count ? ntiles : 2 * ctx->sm_count;
+    gemm_tma_nt_kernel<<<ctas, (TCONSUMERS + 1) * 32, kTSmem, ctx->stream>>>(mapA, mapB, a);
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }
