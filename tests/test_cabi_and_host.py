@@ -160,3 +160,55 @@ def test_two_rank_gloo_maxloc_matches_single_process(tmp_path):
     for p, out in zip(procs, outs):
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+# ---------------------------------------------------------------------------------------------
+# property tests (hypothesis): the sharded reduction equals the reference's first-arg-max on the whole array
+# ---------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(min_value=1, max_value=10 ** 10), st.integers(min_value=1, max_value=16))
+def test_shard_range_partitions_any_count(total, world):
+    from bayesian_optimisation_b200.sharding import shard_range
+    edges = [shard_range(total, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+    assert all(0 <= e - b <= -(-total // world) for b, e in edges)
+
+
+_scores = st.lists(st.one_of(st.sampled_from([0.0, 1.0, -1.0, 2.5, float("-inf")]), st.floats(allow_nan=False, width=16)),
+                   min_size=1, max_size=60)
+
+
+@settings(max_examples=300, deadline=None)
+@given(_scores, st.integers(min_value=1, max_value=9))
+def test_sharded_maxloc_equals_numpy_first_argmax(scores, world):
+    """Every rank reports (its maximum, its FIRST position of it); reduce_pairs over the ranks must give what
+    np.argwhere(a == np.amax(a))[0] gives on the whole array (point_selector.py:207), ties included."""
+    import numpy as np
+    from bayesian_optimisation_b200.sharding import reduce_pairs, shard_range, NO_INDEX
+    a = np.array(scores, dtype=np.float64)
+    pairs = []
+    for r in range(world):
+        b, e = shard_range(len(a), r, world)
+        if e > b:
+            loc = int(np.flatnonzero(a[b:e] == a[b:e].max())[0])
+            pairs.append((float(a[b + loc]), b + loc))
+        else:
+            pairs.append((float("-inf"), NO_INDEX))
+    s, i = reduce_pairs(pairs)
+    want = int(np.argwhere(a == np.amax(a))[0][0])
+    if np.isneginf(a).all():
+        assert s == float("-inf")           # nothing beats the initial value: no index is reported
+    else:
+        assert (s, i) == (float(a[want]), want)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(min_value=1, max_value=5000), st.integers(min_value=1, max_value=16))
+def test_restart_slices_partition_the_restarts(total, world):
+    from bayesian_optimisation_b200.sharding import restart_slice
+    seen = sorted(i for r in range(world) for i in restart_slice(total, r, world))
+    assert seen == list(range(total))
