@@ -212,3 +212,70 @@ def test_restart_slices_partition_the_restarts(total, world):
     from bayesian_optimisation_b200.sharding import restart_slice
     seen = sorted(i for r in range(world) for i in restart_slice(total, r, world))
     assert seen == list(range(total))
+
+
+# ---------------------------------------------------------------------------------------------
+# the kernel function's exp: the constants of csrc/common.cuh, restated in C (same operations, libm fma) and
+# checked against long-double expl on the host -- pins the table and the coefficients without a GPU
+# ---------------------------------------------------------------------------------------------
+_EXP_C = r"""
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+static const double tab[64] = { %(table)s };
+static const double C[8] = { %(coeffs)s };
+static double exp_nonpos(double t) {                 /* csrc/common.cuh: exp_nonpos, operation for operation */
+    const double kd = fma(t, C[0], 6755399441055744.0);
+    int64_t bits; memcpy(&bits, &kd, 8);
+    const int ki = (int)(uint32_t)bits;
+    const double kf = kd - 6755399441055744.0;
+    double r = fma(kf, C[1], t);
+    r = fma(kf, C[2], r);
+    const double T = tab[ki & 63];
+    double q = fma(C[3], r, C[4]);
+    q = fma(q, r, C[5]);
+    q = fma(q, r, C[6]);
+    q = fma(q, r, 0.5);
+    const double p = fma(r * r, q, r);
+    const double m = fma(T, p, T);
+    int64_t mb; memcpy(&mb, &m, 8);
+    const uint32_t hi = (uint32_t)(mb >> 32) + (((uint32_t)ki << 14) & 0xfff00000u);
+    mb = ((int64_t)hi << 32) | (mb & 0xffffffffLL);
+    double res; memcpy(&res, &mb, 8);
+    return t < -708.0 ? 0.0 : res;
+}
+int main(void) {
+    double worst = 0.0; srand(7);
+    for (long i = 0; i < 3000000; i++) {
+        const double u = rand() / (double)RAND_MAX, v = rand() / (double)RAND_MAX;
+        const double t = (i %% 3 == 0) ? -708.0 * u : ((i %% 3 == 1) ? -45.0 * u * v : -1e-3 * u);
+        const long double ref = expl((long double)t);
+        const double ulp = nextafter((double)ref, INFINITY) - (double)ref;
+        const double e = (double)(fabsl((long double)exp_nonpos(t) - ref) / ulp);
+        if (e > worst) worst = e;
+    }
+    printf("%%.4f %%.17g %%.17g %%.17g %%d\n", worst, exp_nonpos(0.0), exp_nonpos(-0.0), exp_nonpos(-709.0), isnan(exp_nonpos(NAN)) ? 1 : 0);
+    return 0;
+}
+"""
+
+
+def test_kernel_function_exp_constants_give_one_ulp(tmp_path):
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = open(os.path.join(ROOT, "bayesian_optimisation_b200", "csrc", "common.cuh")).read()
+    table = re.search(r"kExp2Tab\[64\] = \{(.*?)\};", src, re.S).group(1)
+    coeffs = re.search(r"kExpC\[8\] = \{(.*?)\};", src, re.S).group(1)
+    coeffs = re.sub(r"//[^\n]*", "", coeffs)
+    assert len(re.findall(r"0x1\.[0-9a-f]+p\+0", table)) == 64
+    c = tmp_path / "exp_nonpos_check.c"
+    c.write_text(_EXP_C % {"table": table, "coeffs": coeffs})
+    exe = tmp_path / "exp_nonpos_check"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(c), "-lm"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    worst, at0, atm0, below, nan_ok = float(out[0]), float(out[1]), float(out[2]), float(out[3]), int(out[4])
+    assert worst <= 1.1, worst                    # maximum error in ulp against long-double expl
+    assert at0 == 1.0 and atm0 == 1.0 and below == 0.0 and nan_ok == 1
