@@ -14,26 +14,42 @@ import bench
 from bayesian_optimisation_b200.engine import GPEngine, CandidateGrid, JITTER_POSTERIOR, ACQ_EI
 from bayesian_optimisation_b200.sharding import allreduce_maxloc, shard_range
 
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=bench.N_OBS)
+ap.add_argument("--dim", type=int, default=bench.DIM)
+ap.add_argument("--grid", type=int, default=bench.GRID_PTS, help="grid points per axis")
+ap.add_argument("--kind", default="ei", choices=["ei", "lcb"])
+ap.add_argument("--per-rank", type=int, default=0, help="score only this many candidates per rank (a slice of every shard); 0 = the whole grid")
+args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 eng = GPEngine(local)
-X, y, ell = bench.synthetic()
-grid = CandidateGrid([np.linspace(0.0, 1.0, bench.GRID_PTS)] * bench.DIM)
+if (args.n, args.dim) == (bench.N_OBS, bench.DIM):
+    X, y, ell = bench.synthetic()
+else:
+    from oracle import gp_oracle as _o           # synthetic inputs only (a tool, not the product path)
+    X, y, ell = _o.synthetic_problem(args.n, args.dim)
+grid = CandidateGrid([np.linspace(0.0, 1.0, args.grid)] * args.dim)
+KIND = ACQ_EI if args.kind == "ei" else 0
 dX, dy = eng.to_device(X), eng.to_device(y)
 f_best = float(y.min())
 b, e = shard_range(grid.size, rank, world)
+if args.per_rank:
+    e = min(e, b + args.per_rank)
+scored = (e - b) if not args.per_rank else args.per_rank * world
 # warm-up (kernel attributes, workspaces) on a small slice
-fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR); eng.acquire(fit, grid, b, b + 131072, kind=ACQ_EI, f_best=f_best); fit.close()
+fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR); eng.acquire(fit, grid, b, min(e, b + 65536), kind=KIND, f_best=f_best); fit.close()
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter(); e0.record()
 fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
-res = eng.acquire(fit, grid, b, e, kind=ACQ_EI, f_best=f_best)
+res = eng.acquire(fit, grid, b, e, kind=KIND, f_best=f_best)
 score, index = allreduce_maxloc(res.best_score, res.best_index, device=dev) if world > 1 else (res.best_score, res.best_index)
 e1.record(); torch.cuda.synchronize()
 wall = time.perf_counter() - t0
@@ -42,9 +58,11 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     coords = np.unravel_index(index, grid.shape)
-    print(json.dumps({"config": "N=4096, d=8, EI over the full 10^8-point grid", "n_gpus": world, "candidates": grid.size,
+    total = grid.size if not args.per_rank else scored
+    print(json.dumps({"config": f"N={args.n}, d={args.dim}, {args.kind.upper()} over " + (f"the full {args.grid}^{args.dim}-point grid" if not args.per_rank else f"{args.per_rank} candidates per rank of the {args.grid}^{args.dim}-point grid"),
+                      "n_gpus": world, "candidates": total,
                       "device_seconds_max_over_ranks": float(ms.item()) * 1e-3, "wall_seconds_rank0": wall,
-                      "candidates_per_s": grid.size / (float(ms.item()) * 1e-3), "best_score": score, "best_flat_index": int(index),
+                      "candidates_per_s": total / (float(ms.item()) * 1e-3), "fit_ms_included": True, "best_score": score, "best_flat_index": int(index),
                       "best_grid_index": [int(c) for c in coords], "nlml": fit.nlml, "tensor_path": eng.acquire_path}))
 fit.close()
 if world > 1:
