@@ -9,9 +9,12 @@
 //   k[j,c]  = 2^{1}    * sum_q b_q[j,c] 2^{-7-8q}      b_q in [-128,127]   fixed point with 55 fraction bits)
 //   V[i,c]  = 2^{e_i+1-14} * sum_t 2^{-8t} S_t[i,c],   S_t = sum_{p+q=t} sum_j a_p[i,j] b_q[j,c]   (int32, exact)
 //
-// Levels t = 0..7 are kept (34 digit pairs); the dropped levels t >= 8 are below 2^-50 of the
-// row scale in the worst case -- smaller than the rounding error of an fp64 dot product of the
-// same length.  |S_t| <= 7 * K * 2^14 < 2^31 for K <= 16384, so int32 accumulation never overflows.
+// Levels t = 0..7 are kept (34 digit pairs).  The dropped levels t >= 8 amount to at most 5 K 2^-62 of the
+// row scale 2^{e_i} in the worst case (2^-47.7 at K = 4096, every digit extreme and aligned) and to about
+// 2^-56 for real data, where the level sums are random walks; with the 2^-55 fixed-point rounding of the
+// operands the result stays inside the worst-case rounding error of an fp64 dot product of the same length
+// (tests/test_digit_slices.py checks the scheme against exact rational arithmetic on the host).
+// |S_t| <= 7 * K * 2^14 < 2^31 for K <= 16384, so int32 accumulation never overflows.
 // Because the integer sums are exact, V does not depend on any summation order: the result is
 // bit-reproducible across tiles, chunks and GPUs by construction.
 //

@@ -75,3 +75,17 @@ def test_level_sums_cannot_overflow_int32_at_the_supported_sizes():
     assert 7 * 8192 * 128 * 255 < 2 ** 31
     assert 7 * 16384 * 2 ** 14 < 2 ** 31
     assert 7 * 16384 * 128 * 255 >= 2 ** 31          # why the unsigned variant stops at 8192 rows
+
+
+@pytest.mark.parametrize("K", [512, 4096, 8192])
+def test_worst_case_of_the_dropped_levels_is_5K_2pow_minus_62_of_the_row_scale(K):
+    """Adversarial digits (every W digit +127, every panel byte 255): the dropped levels t = 8..12 then reach their
+    maximum, which the documentation states as 5 K 2^-62 of the row scale 2^e."""
+    a = np.full((SLICES, K), 127, dtype=np.int64)
+    b = np.full((SLICES, K), 255, dtype=np.int64)
+    dropped = Fraction(0)
+    for t in range(8, 2 * SLICES - 1):
+        s = sum(int(a[p] @ b[t - p]) for p in range(SLICES) if 0 <= t - p < SLICES)
+        dropped += Fraction(s) * Fraction(2) ** (-14 - 8 * t) * 2          # relative to the row scale 2^e: 2^{e+1-14-8t} / 2^e
+    assert dropped <= Fraction(5 * K) * Fraction(2) ** -62 * Fraction(101, 100)
+    assert dropped >= Fraction(5 * K) * Fraction(2) ** -62 * Fraction(95, 100)
