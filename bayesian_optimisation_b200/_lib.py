@@ -36,12 +36,25 @@ class Candidates(C.Structure):
                 ("c_total", C.c_int64), ("cross_jitter", C.c_double)]
 
 
+class HostCandidates(C.Structure):
+    """struct bogp_host_candidates (include/bogp.h)."""
+    _fields_ = [("h_points", C.c_void_p), ("h_axes", C.c_void_p), ("h_axis_len", C.POINTER(C.c_int32)),
+                ("c_total", C.c_int64), ("cross_jitter", C.c_double)]
+
+
+class Result(C.Structure):
+    """struct bogp_result (include/bogp.h): the 24-byte device record of a sweep's winner."""
+    _fields_ = [("score", C.c_double), ("index", C.c_int64), ("nan_flag", C.c_int32), ("reserved", C.c_int32)]
+
+
 _vp, _i64, _i32, _dbl, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_size_t
+_pd, _pi64 = C.POINTER(C.c_double), C.POINTER(C.c_int64)
 
 # name -> (restype, argtypes); every symbol include/bogp.h declares
 SIGNATURES = {
     "bogp_version": (C.c_char_p, []),
     "bogp_last_error": (C.c_char_p, []),
+    "bogp_device_count": (_i32, [C.POINTER(_i32)]),
     "bogp_create": (_i32, [_i32, C.POINTER(_vp)]),
     "bogp_destroy": (None, [_vp]),
     "bogp_set_stream": (_i32, [_vp, _vp]),
@@ -51,6 +64,7 @@ SIGNATURES = {
     "bogp_get_acquire_path": (_i32, [_vp]),
     "bogp_profile": (_i32, [_vp, _i32]),
     "bogp_profile_read": (_i32, [_vp, _i32, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "bogp_measure_peak": (_i32, [_vp, _i32, _dbl, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "bogp_kernel_matrix": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _dbl, _vp, _i64]),
     "bogp_fit_workspace_bytes": (_sz, [_i64, _i32]),
     "bogp_fit_create": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _dbl, _vp, _sz, C.POINTER(_vp), C.POINTER(_dbl)]),
@@ -66,9 +80,24 @@ SIGNATURES = {
     "bogp_acquire_workspace_bytes": (_sz, [_vp, _i64]),
     "bogp_acquire": (_i32, [_vp, _vp, C.POINTER(Candidates), _i64, _i64, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp,
                             _vp, _sz, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "bogp_acquire_async": (_i32, [_vp, _vp, C.POINTER(Candidates), _i64, _i64, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp,
+                                  _vp, _sz, _vp]),
+    "bogp_reduce_results": (_i32, [_vp, _vp, _i32, _vp, _pd, _pi64]),
+    "bogp_score_argmax_async": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _vp, _vp]),
     "bogp_score_argmax": (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "bogp_nlml_batched_workspace_bytes": (_sz, [_i64, _i32, _i64, _i32]),
     "bogp_nlml_batched": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _dbl, _vp, _vp, _vp, _sz]),
+    "bogp_session_create": (_i32, [C.POINTER(_i32), _i32, C.POINTER(_vp)]),
+    "bogp_session_destroy": (None, [_vp]),
+    "bogp_session_device_count": (_i32, [_vp]),
+    "bogp_session_ctx": (_vp, [_vp, _i32]),
+    "bogp_session_launch_count": (_i64, [_vp]),
+    "bogp_session_set_acquire_path": (_i32, [_vp, _i32]),
+    "bogp_session_kernel_matrix": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _dbl, _vp]),
+    "bogp_session_nlml": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _dbl, _vp, _vp]),
+    "bogp_session_update": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _dbl, C.POINTER(HostCandidates), _i64, _i64, _dbl,
+                                   _i32, _dbl, _dbl, _vp, _vp, _vp, _pd, _pd, _pi64]),
+    "bogp_session_score": (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp, _pd, _pi64]),
 }
 
 _lib = None

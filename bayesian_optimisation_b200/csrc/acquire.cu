@@ -271,14 +271,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs f) {
 
 // acquisition + arg-max on mu/sigma already on the device (lower_confidence_bound, :197-207)
 __global__ void __launch_bounds__(256) score_kernel(const double* __restrict__ mu, const double* __restrict__ sigma, int64_t c,
-                                                    int kind, double explore, double f_best, double* acq_out,
+                                                    int64_t index_offset, int kind, double explore, double f_best, double* acq_out,
                                                     double* block_score, long long* block_index, int* nan_flag) {
     double best = -INFINITY; long long bi = kNoIndex;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < c; i += (int64_t)gridDim.x * 256) {
         double s = acquisition_value(kind, mu[i], sigma[i], explore, f_best);
         if (acq_out) acq_out[i] = s;
         if (s != s) { atomicExch(nan_flag, 1); continue; }
-        if (better(s, i, best, bi)) { best = s; bi = i; }
+        if (better(s, i + index_offset, best, bi)) { best = s; bi = i + index_offset; }
     }
     block_argmax(best, bi, block_score, block_index, blockIdx.x);
 }
@@ -307,6 +307,32 @@ __global__ void init_best_kernel(double* best, long long* besti, int* nan_flag) 
     best[0] = -INFINITY; besti[0] = kNoIndex; nan_flag[0] = 0;
 }
 
+// bogp_result records (24 bytes: score, index, nan flag) gathered from several sweeps / ranks -> one record
+__global__ void __launch_bounds__(256) reduce_results_kernel(const bogp_result* __restrict__ in, int count, bogp_result* __restrict__ out) {
+    __shared__ double ws[8]; __shared__ long long wi[8]; __shared__ int wn;
+    if (threadIdx.x == 0) wn = 0;
+    __syncthreads();
+    double s = -INFINITY; long long i = kNoIndex; int nanf = 0;
+    for (int b = threadIdx.x; b < count; b += 256) {
+        const double bs = in[b].score; const long long bi = in[b].index;
+        nanf |= in[b].nan_flag;
+        if (better(bs, bi, s, i)) { s = bs; i = bi; }
+    }
+    if (nanf) atomicOr(&wn, 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, s, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (better(os, oi, s, i)) { s = os; i = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; wi[threadIdx.x >> 5] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) if (better(ws[w], wi[w], s, i)) { s = ws[w]; i = wi[w]; }
+        out->score = s; out->index = i; out->nan_flag = wn; out->reserved = 0;
+    }
+}
+
 // Workspace of one chunk of S candidates.  The layout is sized for the larger of the two tensor
 // paths (FP64: 8 B per panel entry, 256-row blocks; INT8: 7 B per entry, 128-row blocks) so that a
 // workspace is valid whichever path is selected.
@@ -333,11 +359,13 @@ extern "C" size_t bogp_acquire_workspace_bytes(const bogp_fit* fit, int64_t max_
     return acq_layout(bogp_fit_n_pad(fit), max_chunk).total;
 }
 
-extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand, int64_t c_begin, int64_t c_end,
-                            int kind, double explore, double f_best, double prior_diag, double* d_mu_out,
-                            double* d_sigma_out, double* d_acq_out, void* d_workspace, size_t workspace_bytes,
-                            double* h_best_score, int64_t* h_best_index) {
-    if (!ctx || !fit || !cand || !d_workspace || c_begin < 0 || c_end <= c_begin || c_end > cand->c_total ||
+// All device work of one sweep, enqueued on ctx->stream without any host synchronisation.  The running winner lives in
+// the caller's 24-byte device record `d_result` (score, index, nan flag).
+static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand, int64_t c_begin, int64_t c_end,
+                           int kind, double explore, double f_best, double prior_diag, double* d_mu_out,
+                           double* d_sigma_out, double* d_acq_out, void* d_workspace, size_t workspace_bytes,
+                           bogp_result* d_result) {
+    if (!ctx || !fit || !cand || !d_workspace || !d_result || c_begin < 0 || c_end <= c_begin || c_end > cand->c_total ||
         (kind != BOGP_ACQ_LCB && kind != BOGP_ACQ_EI)) {
         set_error("bogp_acquire: bad argument"); return BOGP_ERR_BAD_ARG;
     }
@@ -372,8 +400,8 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
         BOGP_CUDA_CHECK(cudaFuncSetAttribute(trigemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmem));
     }
     cudaStream_t st = ctx->stream;
-    double* best = ctx->d_scalars; long long* besti = reinterpret_cast<long long*>(ctx->d_scalars + 1);
-    int* nan_flag = ctx->d_flags;
+    double* best = &d_result->score; long long* besti = reinterpret_cast<long long*>(&d_result->index);
+    int* nan_flag = &d_result->nan_flag;
     init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
 
     // the int32 level sums of the digit-slice product are overflow-free up to K = 16384 (7 * K * 2^14 < 2^31);
@@ -463,36 +491,67 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
             if (rc) return rc;
         }
     }
-    if (h_best_score || h_best_index) {
-        double hs; long long hi; int hn;
-        BOGP_CUDA_CHECK(cudaMemcpyAsync(&hs, best, 8, cudaMemcpyDeviceToHost, st));
-        BOGP_CUDA_CHECK(cudaMemcpyAsync(&hi, besti, 8, cudaMemcpyDeviceToHost, st));
-        BOGP_CUDA_CHECK(cudaMemcpyAsync(&hn, nan_flag, 4, cudaMemcpyDeviceToHost, st));
-        BOGP_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (hn) { set_error("bogp_acquire: NaN acquisition value (reference raises IndexError, point_selector.py:207)"); return BOGP_ERR_NAN_SCORE; }
-        if (h_best_score) *h_best_score = hs;
-        if (h_best_index) *h_best_index = (int64_t)hi;
-    }
+    return BOGP_OK;
+}
+
+static int read_result(bogp_ctx* ctx, const bogp_result* d_result, const char* who, double* h_best_score, int64_t* h_best_index) {
+    bogp_result h;
+    BOGP_CUDA_CHECK(cudaMemcpyAsync(&h, d_result, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BOGP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (h.nan_flag) { set_error("%s: NaN acquisition value (reference raises IndexError, point_selector.py:207)", who); return BOGP_ERR_NAN_SCORE; }
+    if (h_best_score) *h_best_score = h.score;
+    if (h_best_index) *h_best_index = h.index;
+    return BOGP_OK;
+}
+
+extern "C" int bogp_acquire_async(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand, int64_t c_begin, int64_t c_end,
+                                  int kind, double explore, double f_best, double prior_diag, double* d_mu_out,
+                                  double* d_sigma_out, double* d_acq_out, void* d_workspace, size_t workspace_bytes,
+                                  bogp_result* d_result) {
+    return acquire_enqueue(ctx, fit, cand, c_begin, c_end, kind, explore, f_best, prior_diag, d_mu_out, d_sigma_out, d_acq_out,
+                           d_workspace, workspace_bytes, d_result);
+}
+
+extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand, int64_t c_begin, int64_t c_end,
+                            int kind, double explore, double f_best, double prior_diag, double* d_mu_out,
+                            double* d_sigma_out, double* d_acq_out, void* d_workspace, size_t workspace_bytes,
+                            double* h_best_score, int64_t* h_best_index) {
+    if (!ctx) { set_error("bogp_acquire: bad argument"); return BOGP_ERR_BAD_ARG; }
+    bogp_result* slot = reinterpret_cast<bogp_result*>(ctx->d_scalars);
+    const int rc = acquire_enqueue(ctx, fit, cand, c_begin, c_end, kind, explore, f_best, prior_diag, d_mu_out, d_sigma_out, d_acq_out,
+                                   d_workspace, workspace_bytes, slot);
+    if (rc) return rc;
+    if (!h_best_score && !h_best_index) return BOGP_OK;
+    return read_result(ctx, slot, "bogp_acquire", h_best_score, h_best_index);
+}
+
+extern "C" int bogp_reduce_results(bogp_ctx* ctx, const bogp_result* d_results, int count, bogp_result* d_out,
+                                   double* h_best_score, int64_t* h_best_index) {
+    if (!ctx || !d_results || count <= 0) { set_error("bogp_reduce_results: bad argument"); return BOGP_ERR_BAD_ARG; }
+    bogp_result* out = d_out ? d_out : reinterpret_cast<bogp_result*>(ctx->d_scalars + 8);
+    reduce_results_kernel<<<1, 256, 0, ctx->stream>>>(d_results, count, out); BOGP_LAUNCH_CHECK(ctx);
+    if (!h_best_score && !h_best_index) return BOGP_OK;
+    return read_result(ctx, out, "bogp_reduce_results", h_best_score, h_best_index);
+}
+
+extern "C" int bogp_score_argmax_async(bogp_ctx* ctx, const double* d_mu, const double* d_sigma, int64_t c, int64_t index_offset,
+                                       int kind, double explore, double f_best, double* d_acq_out, bogp_result* d_result) {
+    if (!ctx || !d_mu || !d_sigma || !d_result || c <= 0 || (kind != BOGP_ACQ_LCB && kind != BOGP_ACQ_EI)) { set_error("bogp_score_argmax: bad argument"); return BOGP_ERR_BAD_ARG; }
+    cudaStream_t st = ctx->stream;
+    double* best = &d_result->score; long long* besti = reinterpret_cast<long long*>(&d_result->index);
+    int* nan_flag = &d_result->nan_flag;
+    init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
+    int nb = (int)((c + 255) / 256); if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
+    score_kernel<<<nb, 256, 0, st>>>(d_mu, d_sigma, c, index_offset, kind, explore, f_best, d_acq_out, ctx->d_block_score, ctx->d_block_index, nan_flag); BOGP_LAUNCH_CHECK(ctx);
+    merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nb, best, besti); BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;
 }
 
 extern "C" int bogp_score_argmax(bogp_ctx* ctx, const double* d_mu, const double* d_sigma, int64_t c, int kind, double explore,
                                  double f_best, double* d_acq_out, double* h_best_score, int64_t* h_best_index) {
-    if (!ctx || !d_mu || !d_sigma || c <= 0 || (kind != BOGP_ACQ_LCB && kind != BOGP_ACQ_EI)) { set_error("bogp_score_argmax: bad argument"); return BOGP_ERR_BAD_ARG; }
-    cudaStream_t st = ctx->stream;
-    double* best = ctx->d_scalars; long long* besti = reinterpret_cast<long long*>(ctx->d_scalars + 1);
-    int* nan_flag = ctx->d_flags;
-    init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
-    int nb = (int)((c + 255) / 256); if (nb > 2 * ctx->sm_count) nb = 2 * ctx->sm_count;
-    score_kernel<<<nb, 256, 0, st>>>(d_mu, d_sigma, c, kind, explore, f_best, d_acq_out, ctx->d_block_score, ctx->d_block_index, nan_flag); BOGP_LAUNCH_CHECK(ctx);
-    merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nb, best, besti); BOGP_LAUNCH_CHECK(ctx);
-    double hs; long long hi; int hn;
-    BOGP_CUDA_CHECK(cudaMemcpyAsync(&hs, best, 8, cudaMemcpyDeviceToHost, st));
-    BOGP_CUDA_CHECK(cudaMemcpyAsync(&hi, besti, 8, cudaMemcpyDeviceToHost, st));
-    BOGP_CUDA_CHECK(cudaMemcpyAsync(&hn, nan_flag, 4, cudaMemcpyDeviceToHost, st));
-    BOGP_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (hn) { set_error("bogp_score_argmax: NaN acquisition value (reference raises IndexError, point_selector.py:207)"); return BOGP_ERR_NAN_SCORE; }
-    if (h_best_score) *h_best_score = hs;
-    if (h_best_index) *h_best_index = (int64_t)hi;
-    return BOGP_OK;
+    if (!ctx) { set_error("bogp_score_argmax: bad argument"); return BOGP_ERR_BAD_ARG; }
+    bogp_result* slot = reinterpret_cast<bogp_result*>(ctx->d_scalars);
+    const int rc = bogp_score_argmax_async(ctx, d_mu, d_sigma, c, 0, kind, explore, f_best, d_acq_out, slot);
+    if (rc) return rc;
+    return read_result(ctx, slot, "bogp_score_argmax", h_best_score, h_best_index);
 }

@@ -14,8 +14,17 @@ void set_error(const char* fmt, ...) {
 
 using namespace bogp;
 
-extern "C" const char* bogp_version(void) { return "bogp 1 sm_100a"; }
+extern "C" const char* bogp_version(void) { return "bogp 2 sm_100a"; }
 extern "C" const char* bogp_last_error(void) { return g_error; }
+
+extern "C" int bogp_device_count(int* out) {
+    if (!out) { set_error("bogp_device_count: null output pointer"); return BOGP_ERR_BAD_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) { *out = 0; set_error("bogp_device_count: %s", cudaGetErrorString(e)); return BOGP_ERR_CUDA; }
+    *out = count;
+    return BOGP_OK;
+}
 
 extern "C" int bogp_create(int device, bogp_ctx** out) {
     if (!out) { set_error("bogp_create: null output pointer"); return BOGP_ERR_BAD_ARG; }

@@ -17,10 +17,7 @@ import torch
 from . import _lib
 from ._lib import ACQ_EI, ACQ_LCB, BogpError, Candidates
 
-# reference jitters: kernel_rbf adds 1e-4 (point_selector.py:193), update_surrogate another 1e-6 (:78-79)
-JITTER_LML = 1e-4
-PRIOR_DIAG = (1.0 + 1e-4) + 1e-6            # diag of cov_pred, same rounding order as the reference
-JITTER_POSTERIOR = PRIOR_DIAG - 1.0         # exact: 1.0 + JITTER_POSTERIOR == PRIOR_DIAG bit for bit
+from .session import JITTER_LML, JITTER_POSTERIOR, PRIOR_DIAG  # noqa: F401  (the reference's jitters, defined once)
 
 
 @dataclass
@@ -44,11 +41,12 @@ class CandidateGrid:
 
 @dataclass
 class AcquireResult:
-    best_score: float
-    best_index: int
+    best_score: Optional[float]
+    best_index: Optional[int]
     mu: Optional[torch.Tensor] = None
     sigma: Optional[torch.Tensor] = None
     acq: Optional[torch.Tensor] = None
+    record: Optional[torch.Tensor] = None     # sync=False: the 24-byte device record (struct bogp_result) of the winner
 
 
 class GPFit:
@@ -231,11 +229,12 @@ class GPEngine:
     # ------------------------------------------------------------------ K4
     def acquire(self, fit: GPFit, candidates, c_begin: int = 0, c_end: Optional[int] = None, kind: int = ACQ_LCB,
                 explore: float = 4.0, f_best: float = 0.0, prior_diag: float = PRIOR_DIAG, outputs: bool = False,
-                chunk: Optional[int] = None, cross_jitter: float = 0.0) -> AcquireResult:
+                chunk: Optional[int] = None, cross_jitter: float = 0.0, sync: bool = True) -> AcquireResult:
         """Score flat candidate indices [c_begin, c_end) and return the best (score, index).
 
         `candidates`: CandidateGrid, or an explicit (C, d) array (numpy -> copied to HBM, or a
-        CUDA tensor used in place)."""
+        CUDA tensor used in place).  sync=False only enqueues the sweep: the winner stays on the device in
+        `result.record` (for `sharding.allreduce_maxloc_device` / `reduce_records`)."""
         self._sync_stream()
         keep = []
         cd = Candidates()
@@ -268,6 +267,15 @@ class GPEngine:
             mu = torch.empty(count, dtype=torch.float64, device=self.device)
             sigma = torch.empty_like(mu)
             acq = torch.empty_like(mu)
+        if not sync:
+            rec = torch.empty(24, dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.bogp_acquire_async(self._ctx, fit._h, C.byref(cd), int(c_begin), c_end, int(kind), float(explore),
+                                                   float(f_best), float(prior_diag),
+                                                   mu.data_ptr() if outputs else None, sigma.data_ptr() if outputs else None,
+                                                   acq.data_ptr() if outputs else None,
+                                                   self._acq_ws.data_ptr(), need, rec.data_ptr()))
+            self._keepalive = keep        # the sweep is still running: its inputs must outlive this call
+            return AcquireResult(None, None, mu, sigma, acq, rec)
         bs, bi = C.c_double(), C.c_int64()
         code = self.lib.bogp_acquire(self._ctx, fit._h, C.byref(cd), int(c_begin), c_end, int(kind), float(explore),
                                      float(f_best), float(prior_diag),
@@ -279,6 +287,33 @@ class GPEngine:
         _lib.check(code)
         del keep
         return AcquireResult(bs.value, int(bi.value), mu, sigma, acq)
+
+    def empty_record(self) -> torch.Tensor:
+        """The record of a rank that scored nothing: (-inf, no index, no NaN)."""
+        import struct
+        raw = struct.pack("<dqii", float("-inf"), (1 << 63) - 1, 0, 0)
+        return torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone().to(self.device)
+
+    def reduce_records(self, records: torch.Tensor, count: int):
+        """Fold `count` gathered 24-byte records on the device and read the winner (ONE host read).  IndexError if any
+        record carries the NaN flag (point_selector.py:207)."""
+        self._sync_stream()
+        bs, bi = C.c_double(), C.c_int64()
+        code = self.lib.bogp_reduce_results(self._ctx, records.data_ptr(), int(count), None, C.byref(bs), C.byref(bi))
+        if code == _lib.BOGP_ERR_NAN_SCORE:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0 (NaN acquisition value)")
+        _lib.check(code)
+        return bs.value, int(bi.value)
+
+    def measure_peak(self, kind: str, sustain_seconds: float = 0.0):
+        """Issue-rate peak of a pipe on this device (measurement aid, csrc/peaks.cu): "i8" -> int8 TOP/s of back-to-back
+        tcgen05.mma kind::i8, "fp64" -> TFLOP/s of DMMA.8x8x4.  Returns (burst, sustained): best of 5 short launches,
+        and the average over `sustain_seconds` of back-to-back launches (None if 0)."""
+        self._sync_stream()
+        burst, sus = C.c_double(), C.c_double()
+        _lib.check(self.lib.bogp_measure_peak(self._ctx, {"i8": 0, "fp64": 1}[kind], float(sustain_seconds), C.byref(burst),
+                                              C.byref(sus) if sustain_seconds > 0 else None))
+        return burst.value, (sus.value if sustain_seconds > 0 else None)
 
     def score_argmax(self, mu: torch.Tensor, sigma: torch.Tensor, kind: int = ACQ_LCB, explore: float = 4.0,
                      f_best: float = 0.0, want_acq: bool = True) -> AcquireResult:
@@ -318,10 +353,20 @@ class GPEngine:
             return torch.tensor([val], dtype=torch.float64, device=self.device)
         out = torch.empty(r, dtype=torch.float64, device=self.device)
         grad = torch.empty((r, dim), dtype=torch.float64, device=self.device) if want_grad else None
-        need = self.lib.bogp_nlml_batched_workspace_bytes(n, dim, r, 1 if want_grad else 0)
+        # The batched workspace is r * n_pad^2 * 16 B and more (2500 restarts at n = 1024: 42 GB): work through the
+        # restarts in chunks that fit half of the free device memory (at most 24 GB).  Restarts are independent, so
+        # the chunking changes no result.
+        free_b, _ = torch.cuda.mem_get_info(self.device)
+        budget = max(64 << 20, min(free_b // 2, 24 << 30))
+        chunk = r
+        while chunk > 1 and self.lib.bogp_nlml_batched_workspace_bytes(n, dim, chunk, 1 if want_grad else 0) > budget:
+            chunk = (chunk + 1) // 2
+        need = self.lib.bogp_nlml_batched_workspace_bytes(n, dim, chunk, 1 if want_grad else 0)
         ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.bogp_nlml_batched(self._ctx, dx.data_ptr(), dy.data_ptr(), n, dim, de.data_ptr(), r, float(jitter),
-                                              out.data_ptr(), grad.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel()))
+        for r0 in range(0, r, chunk):
+            cur = min(chunk, r - r0)
+            _lib.check(self.lib.bogp_nlml_batched(self._ctx, dx.data_ptr(), dy.data_ptr(), n, dim, de[r0:].data_ptr(), cur, float(jitter),
+                                                  out[r0:].data_ptr(), grad[r0:].data_ptr() if want_grad else None, ws.data_ptr(), ws.numel()))
         torch.cuda.current_stream(self.device).synchronize()
         return (out, grad) if want_grad else out
 

@@ -4,23 +4,34 @@ N=4096 observations, d=8 (BASELINE.json `metric`, configs[2]), plus the GP fit t
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P bench.py --gpus N --steps K --warmup W
+        --master-port P bench.py --gpus N --steps K --warmup W [--scaling strong]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
 
 One "step" = one pass of the hot path over one batch of synthetic input: a full GP fit
 (Gram + Cholesky + log marginal likelihood + W = L^-1) followed by an expected-improvement sweep
-with arg-max over a contiguous slice of `--cands` candidates per GPU of the 10^8-point grid
-(10 points per axis, d=8).  Ranks score disjoint contiguous slices (weak scaling) and exchange
-16 bytes per rank per step to pick the winner.  `value` = candidates scored by all ranks per
-second, timed on the device with CUDA events, max over ranks.
+with arg-max over a contiguous slice of the 10^8-point grid (10 points per axis, d=8).
+  --scaling weak   (default): `--cands` candidates per GPU per step, the slice grows with N;
+  --scaling strong: `--total-cands` candidates per step in total, split over the N ranks
+                    (north_star: "1e8 candidates, EI sharded across 1/2/4/8").
+Ranks score disjoint contiguous slices and exchange ONE 24-byte record per rank per step, device to
+device, to pick the winner.  `value` = candidates scored by all ranks per second, timed on the device
+with CUDA events, max over ranks.  `e2e` = the same through `PointSelector.update_surrogate()` +
+`expected_improvement()` with pageable host numpy arrays (copies inside the timed region).
 """
 from __future__ import annotations
 
+import os
+import sys
+
+# The CPU arm must use every host core also under torchrun (which exports OMP_NUM_THREADS=1): BLAS reads these
+# variables when numpy is first imported, so they are set before that import.
+if "reference" in sys.argv[1:] or "--impl=reference" in sys.argv[1:]:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -91,10 +102,33 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def workload_config(scaling, gpus):
+    """The workload both arms run -- identical in the two JSON lines; what each arm scored per step is stated beside
+    it (`candidates_per_step_per_gpu`, `cpu_baseline.sample`), not inside it."""
+    return {"workload": f"synthetic GP N={N_OBS}, d={DIM}, ell=0.3; per step: GP fit (Gram+Cholesky+LML+L^-1) + EI sweep + arg-max over a "
+                        f"contiguous candidate slice per GPU of the {GRID_PTS}^{DIM}=1e8-point grid (BASELINE.json configs[2])",
+            "n_obs": N_OBS, "dim": DIM, "grid_points_per_axis": GRID_PTS, "acquisition": "EI", "scaling": scaling,
+            "sharding": f"contiguous flat-index slices x{gpus}, Cholesky replicated, one 24-byte (score, index, nan) record per rank, "
+                        "all_gather + fold on the device (max score, then min flat index)",
+            "l2": "per-step working set (k_* panel digits 2 x 0.9 GB + W digits 60 MB, re-streamed per kernel chunk) exceeds the 126 MB L2; no flush needed"}
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's numpy path (chunked, diag-only, inv-based)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample, verbose=False):
+def blas_threads_all_cores():
+    """Pin the BLAS pool to every host core (also under torchrun) and return the thread count actually in use."""
+    want = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return want
+
+
+def cpu_reference_run(steps, warmup, sample):
+    """Restatement of point_selector.py:78-98,166-195 + EI on `sample` grid candidates per step (oracle/gp_oracle.py)."""
     from oracle import gp_oracle as o
     X, y, ell = synthetic()
     axes = [np.linspace(0.0, 1.0, GRID_PTS)] * DIM
@@ -131,65 +165,36 @@ def cpu_reference_run(steps, warmup, sample, verbose=False):
     return sample * steps / dt, dt / steps * 1e3, fit_s * 1e3
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        return os.cpu_count() or 1
-
-
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = args.ref_sample
-    cores = blas_threads()
+    cores = blas_threads_all_cores()
     v, ms, fit_ms = cpu_reference_run(args.steps, args.warmup, sample)
-    desc = (f"oracle port of point_selector.py:78-98,166-195 + EI (numpy, inv-based, chunked diag-only), {sample} grid candidates "
-            f"per step of the same N=4096,d=8 problem; the fit (Gram+inv+slogdet, {fit_ms:.0f} ms) is done once outside the timed steps")
+    desc = (f"oracle port of point_selector.py:78-98,166-195 + EI (numpy, inv-based, chunked diag-only) on {cores} BLAS threads "
+            f"(os.cpu_count() = {os.cpu_count()}): a bounded sample of {sample} grid candidates per step of the same N=4096,d=8 workload "
+            f"(the GPU arm scores {args.cands} per GPU per step); the fit (Gram+inv+slogdet, {fit_ms:.0f} ms) is done once, outside the "
+            "timed steps, which favours the CPU arm")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.cands, args.gpus),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.scaling, args.gpus), "candidates_per_step_per_gpu": sample,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "fit_ms": fit_ms, "gpu_launches": 0}
     emit(line)
 
 
-def workload_config(cands, gpus):
-    return {"workload": f"synthetic GP N={N_OBS}, d={DIM}, ell=0.3; per step: GP fit (Gram+Cholesky+LML+L^-1) + EI sweep + arg-max over a "
-                        f"contiguous {cands}-candidate slice per GPU of the {GRID_PTS}^{DIM}=1e8-point grid (BASELINE.json configs[2])",
-            "n_obs": N_OBS, "dim": DIM, "candidates_per_step_per_gpu": cands, "grid_points_per_axis": GRID_PTS,
-            "acquisition": "EI", "sharding": f"contiguous flat-index slices x{gpus}, Cholesky replicated, 16-byte all_gather max-loc",
-            "l2": "per-step working set (k_* panel 537 MB + W 67 MB, re-streamed per kernel chunk) exceeds the 126 MB L2; no flush needed"}
-
-
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def measure_fp64_peak(torch, dev):
-    """cuBLAS DGEMM 6144^3, best of 5, CUDA events: the FP64 roofline denominator (MEASURED_PEAKS.json has no fp64 entry)."""
-    n = 6144
-    a = torch.randn(n, n, dtype=torch.float64, device=dev)
-    b = torch.randn(n, n, dtype=torch.float64, device=dev)
-    torch.matmul(a, b)
-    torch.cuda.synchronize()
-    best = 1e30
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    del a, b
-    return 2.0 * n ** 3 / best * 1e-9
-
-
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from bayesian_optimisation_b200.engine import GPEngine, CandidateGrid, JITTER_POSTERIOR, ACQ_EI
     from bayesian_optimisation_b200.point_selector import PointSelector
-    from bayesian_optimisation_b200.sharding import allreduce_maxloc, shard_range
+    from bayesian_optimisation_b200 import session as sm
+    from bayesian_optimisation_b200.sharding import allreduce_maxloc_device, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,25 +208,30 @@ def run_gpu_arm(args):
             os.environ["NCCL_DEBUG"] = os.environ["BOGP_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     eng = GPEngine(local)
+    session = sm.Session([local])
+    sm.set_default_session(session)
     if args.path:
         eng.set_acquire_path(args.path)
+        session.set_acquire_path(args.path)
     X, y, ell = synthetic()
     f_best = float(y.min())
     grid = CandidateGrid([np.linspace(0.0, 1.0, GRID_PTS)] * DIM)
-    cands = args.cands
+    strong = args.scaling == "strong"
+    step_total = args.total_cands if strong else world * args.cands          # candidates per step, all ranks
+    cands = -(-step_total // world)                                           # per rank (ceil)
     dX, dy = eng.to_device(X), eng.to_device(y)
 
     def step_range(k):
-        """global slice of step k: world*cands contiguous candidates, split across ranks"""
-        g0 = (k * world * cands) % max(1, grid.size - world * cands)
-        b, e = shard_range(world * cands, rank, world)
+        """this rank's slice of step k: `step_total` contiguous candidates, split across the ranks"""
+        g0 = (k * step_total) % max(1, grid.size - step_total)
+        b, e = shard_range(step_total, rank, world)
         return g0 + b, g0 + e
 
-    def device_step(k):
+    def device_step(k, kind=ACQ_EI, **kw):
         fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
         b, e = step_range(k)
-        res = eng.acquire(fit, grid, b, e, kind=ACQ_EI, f_best=f_best, chunk=args.chunk)
-        s, i = allreduce_maxloc(res.best_score, res.best_index, device=dev) if world > 1 else (res.best_score, res.best_index)
+        res = eng.acquire(fit, grid, b, e, kind=kind, chunk=args.chunk, sync=False, **kw)
+        s, i = allreduce_maxloc_device(eng, res.record)          # world == 1: just the 24-byte read
         fit.close()
         return s, i
 
@@ -230,17 +240,27 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def time_fits(reps):
-        best = 1e30
+        out = []
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); f = eng.fit(dX, dy, ell, JITTER_POSTERIOR); b.record(); torch.cuda.synchronize()
-            best = min(best, a.elapsed_time(b)); f.close()
-        return best
+            out.append(a.elapsed_time(b)); f.close()
+        return out
 
-    # ---- fit time alone, before the sweeps (CUDA events, best of 20 back-to-back fits): the fit is latency-bound and
-    #      follows the SM clock, which stays power-capped for a while after a sweep -- it is timed again after them
-    fit_ms_before = time_fits(20)
+    # ---- measured peaks of the two pipes, cold (burst): the roofline denominators (csrc/peaks.cu)
+    i8_burst, _ = eng.measure_peak("i8")
+    f64_burst, _ = eng.measure_peak("fp64")
+
+    # ---- fit time alone, before the sweeps (CUDA events, 20 back-to-back fits): the fit is latency-bound and follows the
+    #      SM clock, which stays power-capped for a while after a sweep -- it is timed again after them, and THAT is the headline
+    fits_before = time_fits(20)
 
     # ---- device-resident throughput ("value")
     for k in range(args.warmup):
@@ -258,148 +278,137 @@ def run_gpu_arm(args):
         last = device_step(args.warmup + k)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
     launches = eng.launches - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * cands * args.steps / (ms * 1e-3)
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = step_total * args.steps / (ms * 1e-3)
+    fits_after = time_fits(15)
 
     # ---- the reference's own acquisition (explore*sigma - mu, "LCB/UCB", point_selector.py:204) on the same slices:
     #      same sweep, different epilogue; reported beside the EI headline
-    def lcb_step(k):
-        fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
-        b, e = step_range(k)
-        res = eng.acquire(fit, grid, b, e, kind=0, explore=4.0, chunk=args.chunk)
-        out = allreduce_maxloc(res.best_score, res.best_index, device=dev) if world > 1 else (res.best_score, res.best_index)
-        fit.close()
-        return out
-    lcb_step(0)
+    device_step(0, kind=0, explore=4.0)
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
     for k in range(2):
-        lcb_step(1 + k)
+        device_step(1 + k, kind=0, explore=4.0)
     a1.record()
     barrier()
-    tl = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-    lcb_value = world * cands * 2 / (float(tl.item()) * 1e-3)
+    lcb_value = step_total * 2 / (max_over_ranks(a0.elapsed_time(a1)) * 1e-3)
 
-    fit_ms_after = time_fits(10)
-    fit_ms = min(fit_ms_before, fit_ms_after)
+    # ---- end to end through the reference-facing class: pageable host numpy in, host numpy out.  Under torchrun every
+    #      rank hands the WHOLE candidate array of the step to PointSelector, which scores its slice on its GPU, all-gathers
+    #      mu / sigma (every rank ends up with the full arrays, the API of the single-process class) and picks the winner
+    #      with the one-record exchange.
+    e2e_total = min(step_total, args.e2e_cands * world)
+    blocks = [grid_points_host(grid.axes, (k * e2e_total) % (grid.size - e2e_total), (k * e2e_total) % (grid.size - e2e_total) + e2e_total)
+              for k in range(2)]                                   # generated BEFORE the timed region; plain (pageable) numpy arrays
+    e2e_launch0 = [0]
 
-    # ---- end to end through the reference-facing class with HOST buffers
-    # PointSelector: host measured points + host candidate array in, host mean/sigma/acquisition out.
-    e2e_cands = min(cands, args.e2e_cands)
-    # two pinned host candidate blocks, filled BEFORE the timed region (generating synthetic input is not part of the
-    # path); every timed step hands one of them to the drop-in, which copies it to the device itself
-    pinned_blocks = [torch.empty((e2e_cands, DIM), dtype=torch.float64).pin_memory() for _ in range(2)]
     def e2e_step(k):
-        b, _ = step_range(k)
         ps = PointSelector()
-        ps._engine = eng                        # same context / tensor path as the device-resident leg
         ps.name, ps.iteration = "bench", k
         ps.measured_pts, ps.measured_vals = X, y
-        ps.feature_domain = [e2e_cands]
-        ps.predicted_pts = pinned_blocks[k % 2].numpy()
+        ps.feature_domain = [e2e_total]
+        ps.predicted_pts = blocks[k % 2]
         ps.length_scales = np.array([0.3])      # one-point length-scale grid: one LML evaluation (tune_kernel) per step
-        ps.update_surrogate()                   # LML fit + posterior fit + sweep; mu/sigma copied back to host arrays
-        idx = ps.expected_improvement(f_best)   # EI + arg-max; acquisition copied back
-        return int(idx[0]) + b
-    for k in range(2):
-        pinned_blocks[k].numpy()[:] = grid_points_host(grid.axes, step_range(k)[0], step_range(k)[0] + e2e_cands)
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_step(0)
+        ps.update_surrogate()                   # LML fit + posterior fit + sweep; mu / sigma come back as host arrays
+        idx = ps.expected_improvement(f_best)   # EI + arg-max on the device copy; acquisition comes back as a host array
+        return int(idx[0])
+    e2e_step(0); e2e_step(1)
     barrier()
+    e2e_launch0[0] = session.launches
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
+    for k in range(args.steps):
         e2e_step(k)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_cands * e2e_steps / float(t.item())
-    h2d = (N_OBS * DIM + N_OBS) * 8 * 2 + e2e_cands * DIM * 8 + 2 * DIM * 8
-    d2h = 3 * e2e_cands * 8 + 8 + 16 + 16
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_launches = session.launches - e2e_launch0[0]
+    e2e_value = e2e_total * args.steps / e2e_s
+    b_, e_ = shard_range(e2e_total, rank, world)
+    h2d = (N_OBS * DIM + N_OBS) * 8 * 2 + (e_ - b_) * DIM * 8 + 2 * DIM * 8                 # X, y twice (LML fit, posterior fit), this rank's slice, ell
+    d2h = 3 * (e_ - b_) * 8 + 8 + 2 * 24                                                    # mu, sigma, EI of the slice, nlml, two winner records
+    if world > 1:       # the slices go back up for the NCCL all_gather and the full arrays come down on every rank
+        h2d += 3 * (e_ - b_) * 8
+        d2h += 3 * e2e_total * 8
 
-    # ---- roofline of the dominant kernel (the acquisition product V = L^-1 k_*), per-launch CUDA-event
-    #      timing in a separate pass (the hooks serialise the stream, so never inside the timed steps)
-    roof, cpu_base, fp64_peak = None, None, None
+    # ---- roofline of the dominant kernel (the acquisition product V = L^-1 k_*), per-launch CUDA-event timing in a separate
+    #      pass (the hooks serialise the stream, so never inside the timed steps), and of the fit
+    roof = roof_fit = cpu_base = None
     if rank == 0:
         fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
         eng.profile(True)
-        eng.acquire(fit, grid, 0, min(cands, 16 * args.chunk), kind=ACQ_EI, f_best=f_best, chunk=args.chunk)
+        prof_cands = min(cands, 16 * args.chunk)
+        eng.acquire(fit, grid, 0, prof_cands, kind=ACQ_EI, f_best=f_best, chunk=args.chunk)
         prof = {k: v for k, v in eng.profile_read().items() if k in ("panel", "trigemm", "finalize", "merge")}
         eng.profile(False)
         n_pad = fit.n_pad
         fit.close()
-        fp64_peak = measure_fp64_peak(torch, dev)
+        i8_hot, i8_sus = eng.measure_peak("i8", 0.5)               # right after the serialised sweep: same thermal state
+        f64_hot, f64_sus = eng.measure_peak("fp64", 0.3)
         tri_ms, tri_n = prof["trigemm"]
         per_launch_ms = tri_ms / max(1, tri_n)
-        chunk_c = min(args.chunk, cands)
-        flops = float(N_OBS) ** 2 * chunk_c                      # N^2 fp64 flops per candidate (triangular product)
+        launch_c = prof_cands // max(1, tri_n)                       # candidates per tri-GEMM launch (profiling runs unpipelined chunks)
+        flops = float(N_OBS) ** 2 * launch_c                         # N^2 fp64 flops per candidate (triangular product)
         fp64_equiv = flops / (per_launch_ms * 1e-3) * 1e-12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        traffic = None
+        traffic, tnote = None, None
         tj = os.path.join(ROOT, "profiles", "trigemm_traffic.json")
         if os.path.isfile(tj):
             try:
-                traffic = json.load(open(tj)).get(eng.acquire_path, {}).get("dram_bytes_per_launch")
+                rec = json.load(open(tj)).get(eng.acquire_path, {})
+                if int(rec.get("candidates_per_launch", -1)) == int(launch_c):
+                    traffic, tnote = rec.get("dram_bytes_per_launch"), rec.get("source")
+                else:
+                    tnote = f"no ncu capture of a {launch_c}-candidate launch under profiles/ (the stored one is {rec.get('candidates_per_launch')})"
             except Exception:
-                traffic = None
+                pass
         total_prof = sum(v[0] for v in prof.values())
         share = {k: v[0] / total_prof for k, v in prof.items()} if total_prof > 0 else None
+        peaks = {"int8_umma_burst_tops": i8_burst, "int8_umma_after_sweep_tops": i8_hot, "int8_umma_sustained_0.5s_tops": i8_sus,
+                 "fp64_dmma_burst_tflops": f64_burst, "fp64_dmma_after_sweep_tflops": f64_hot, "fp64_dmma_sustained_0.3s_tflops": f64_sus,
+                 "how": "bogp_measure_peak (csrc/peaks.cu): issue-rate loops on this GPU in this run; burst = best of 5 launches before any sweep"}
         if eng.acquire_path == "i8":
             # executed integer work: 34 digit pairs x n_pad*(n_pad+128)/2 MACs per candidate, 2 ops per MAC
-            int8_ops = 34.0 * n_pad * (n_pad + 128) * chunk_c
+            int8_ops = 34.0 * n_pad * (n_pad + 128) * launch_c
             achieved = int8_ops / (per_launch_ms * 1e-3) * 1e-12
-            bf16 = peaks.get("bf16_tflops")
-            peak = 2.0 * bf16 if bf16 else 2.0 * 1590.0
             roof = {"bound": "tensor", "kernel": "trigemm_i8_kernel (tcgen05.mma kind::i8, TMEM accumulators; exact digit-slice fp64 product)",
-                    "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic,
-                    "ms_per_launch": per_launch_ms, "launches_timed": tri_n, "executed_int8_ops_per_launch": int8_ops,
-                    "algorithmic_flops_per_launch": flops, "fp64_equivalent_tflops": fp64_equiv,
-                    "fp64_pipe_peak_tflops": max(fp64_peak, 37.0), "frac_of_fp64_pipe_peak": fp64_equiv / max(fp64_peak, 37.0),
-                    "frac_of_nominal_int8_peak": achieved / 4500.0,
-                    "ncu_utcimma_int8_pct_of_peak": (json.load(open(tj)).get("i8", {}).get("utcimma_int8_ops_pct_of_peak") if os.path.isfile(tj) else None),
-                    "peak_source": ("dense int8 tensor peak taken as 2 x the measured cuBLAS bf16 burst figure of MEASURED_PEAKS.json "
-                                    f"({bf16} TF/s; int8 runs at twice the bf16 rate, nominal 4500 vs 2250) -- of measured"
-                                    if bf16 else "2 x the fallback bf16 figure 1590 TF/s -- of fallback"),
-                    "share_of_sweep": share}
+                    "achieved": achieved, "peak": i8_burst, "unit": "TOP/s", "frac": achieved / i8_burst, "traffic": traffic, "traffic_source": tnote,
+                    "frac_of_sustained_peak": achieved / i8_sus, "ms_per_launch": per_launch_ms, "launches_timed": tri_n,
+                    "candidates_per_launch": launch_c, "executed_int8_ops_per_launch": int8_ops, "algorithmic_flops_per_launch": flops,
+                    "fp64_equivalent_tflops": fp64_equiv, "frac_of_fp64_pipe_peak": fp64_equiv / f64_burst,
+                    "peak_source": "of measured: int8 tcgen05.mma issue-rate peak of THIS GPU (burst, max clocks), measured in this run; "
+                                   "MEASURED_PEAKS.json has no int8 entry", "peaks": peaks, "share_of_sweep": share}
         else:
-            dmma_peak = 37.0                                      # DMMA issue-rate peak measured with tools/dmma_bench (profiles/)
-            peak = max(fp64_peak, dmma_peak)
-            roof = {"bound": "tensor", "kernel": "trigemm_kernel (FP64 DMMA)", "achieved": fp64_equiv, "peak": peak, "unit": "TFLOP/s",
-                    "frac": fp64_equiv / peak, "traffic": traffic, "ms_per_launch": per_launch_ms, "launches_timed": tri_n,
-                    "algorithmic_flops_per_launch": flops,
-                    "peak_source": f"fp64 is not in MEASURED_PEAKS.json: max(cuBLAS DGEMM 6144^3 measured live = {fp64_peak:.1f} TF/s, "
-                                   f"DMMA.8x8x4 issue-rate microbenchmark tools/dmma_bench = {dmma_peak} TF/s)",
-                    "share_of_sweep": share}
+            roof = {"bound": "tensor", "kernel": "trigemm_kernel (FP64 DMMA)", "achieved": fp64_equiv, "peak": f64_burst, "unit": "TFLOP/s",
+                    "frac": fp64_equiv / f64_burst, "traffic": traffic, "traffic_source": tnote, "ms_per_launch": per_launch_ms,
+                    "launches_timed": tri_n, "candidates_per_launch": launch_c, "algorithmic_flops_per_launch": flops,
+                    "peak_source": "of measured: DMMA.8x8x4 issue-rate peak of THIS GPU, measured in this run", "peaks": peaks, "share_of_sweep": share}
+        fit_ms_head = float(np.median(fits_after))
+        fit_flops = float(N_OBS) ** 3 / 3.0
+        roof_fit = {"bound": "tensor", "kernel": "GP fit: gram + blocked Cholesky (DMMA SYRK) + L^-1 + alpha + nlml", "unit": "TFLOP/s",
+                    "achieved": fit_flops / (fit_ms_head * 1e-3) * 1e-12, "peak": f64_burst, "frac": fit_flops / (fit_ms_head * 1e-3) * 1e-12 / f64_burst,
+                    "algorithmic_flops": fit_flops, "note": "SURVEY 8d: N^3/3 flops per fit (the N^3/3 of the triangular inverse is extra work the "
+                    "design adds and is not counted); latency-bound by the serial chain of diagonal blocks at this N", "ms": fit_ms_head}
         if world == 1 and not args.no_cpu_baseline:
-            cores = blas_threads()
+            cores = blas_threads_all_cores()
             v, _, cfit = cpu_reference_run(2, 1, args.ref_sample)
             cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"oracle port (numpy, inv-based, chunked diag-only) of the same N=4096,d=8 EI sweep on {args.ref_sample} grid candidates x 2 steps; "
-                                  f"its fit (Gram+inv+slogdet) took {cfit:.0f} ms once, outside the timed sample"}
+                        "sample": f"oracle port (numpy, inv-based, chunked diag-only) of the same N=4096,d=8 EI sweep on {args.ref_sample} grid candidates x 2 steps, "
+                                  f"{cores} BLAS threads; its fit (Gram+inv+slogdet) took {cfit:.0f} ms once, outside the timed sample"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": dict(workload_config(cands, world), tensor_path=eng.acquire_path), "fit_ms": fit_ms,
-                "fit_ms_after_sweeps": fit_ms_after, "lcb_candidates_per_s": lcb_value,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": dict(workload_config(args.scaling, world), tensor_path=eng.acquire_path),
+                "candidates_per_step_per_gpu": cands, "candidates_per_step": step_total,
+                "fit_ms": float(np.median(fits_after)), "fit_ms_best": float(min(fits_before + fits_after)),
+                "fit_ms_before_sweeps_median": float(np.median(fits_before)), "fit_ms_after_sweeps_median": float(np.median(fits_after)),
+                "lcb_candidates_per_s": lcb_value,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "PointSelector.update_surrogate() + expected_improvement() with host numpy buffers", "candidates_per_step_per_gpu": e2e_cands,
-                        "steps": e2e_steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+                        "api": "PointSelector.update_surrogate() + expected_improvement(): pageable host numpy arrays in and out through the "
+                               "host-buffer C ABI (bogp_session_*)" + ("; one process per GPU, slices all-gathered, one-record max-loc exchange" if world > 1 else ""),
+                        "candidates_per_step": e2e_total, "steps": args.steps, "gpu_launches": e2e_launches},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_fit": roof_fit, "cpu_baseline": cpu_base,
                 "selected": {"score": last[0], "flat_index": last[1]}}
         emit(line)
     if world > 1:
@@ -431,9 +440,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cands", type=int, default=1 << 20, help="candidates per step per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cands", type=int, default=1 << 20, help="weak scaling: candidates per step per GPU")
+    ap.add_argument("--total-cands", type=int, default=1 << 23, help="strong scaling: candidates per step, all GPUs together")
     ap.add_argument("--chunk", type=int, default=65536, help="candidates per kernel chunk (two half-chunks are pipelined)")
-    ap.add_argument("--e2e-cands", type=int, default=1 << 20)
+    ap.add_argument("--e2e-cands", type=int, default=1 << 20, help="end-to-end leg: candidates per step per GPU (at most)")
     ap.add_argument("--ref-sample", type=int, default=8192, help="candidates per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", default=None, choices=["i8", "fp64"], help="tensor path of the acquisition product (default: library default, i8)")

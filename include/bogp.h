@@ -44,6 +44,9 @@ typedef struct bogp_ctx bogp_ctx;
 const char* bogp_version(void);
 const char* bogp_last_error(void);
 
+/* number of CUDA devices visible to this process (0 and BOGP_ERR_CUDA without a driver) */
+int  bogp_device_count(int* out);
+
 /* One context per process and device.  Allocates a few KB of device scratch. */
 int  bogp_create(int device, bogp_ctx** out);
 void bogp_destroy(bogp_ctx* ctx);
@@ -68,6 +71,15 @@ int bogp_get_acquire_path(const bogp_ctx* ctx);
  * region).  kernel_id: 0 panel, 1 tri-GEMM, 2 finalize, 3 merge.                            */
 int bogp_profile(bogp_ctx* ctx, int enable);
 int bogp_profile_read(const bogp_ctx* ctx, int kernel_id, double* ms_total, int64_t* launches);
+
+/* Measurement aid (bench.py's roofline denominators; never on the product path): the issue-rate peak of one
+ * pipe, measured on this device with CUDA events: burst = best of 5 launches (a few ms each) after a warm-up;
+ * sustained (optional) = average over back-to-back launches for sustain_seconds, i.e. under the power cap.
+ *   BOGP_PEAK_I8_UMMA   back-to-back tcgen05.mma kind::i8 (M=128,N=256,K=32) on every SM -> int8 TOP/s
+ *   BOGP_PEAK_F64_DMMA  independent DMMA.8x8x4 chains, 16 warps per SM                    -> fp64 TFLOP/s   */
+#define BOGP_PEAK_I8_UMMA       0
+#define BOGP_PEAK_F64_DMMA      1
+int bogp_measure_peak(bogp_ctx* ctx, int kind, double sustain_seconds, double* h_burst_tera, double* h_sustained_tera);
 
 /* ---- K1: ARD squared-exponential Gram matrix ------------------- point_selector.py:166-195
  * K[i,j] = exp(-0.5 * sum_k (a_ik-b_jk)^2 / ell_k^2) (+ jitter where i == j), row-major,
@@ -128,6 +140,15 @@ typedef struct bogp_candidates {
                                      (point_selector.py:173-177 applied at :81); else 0   */
 } bogp_candidates;
 
+/* Winner of a sweep as it lives on the DEVICE (24 bytes): what ranks exchange in the multi-GPU mode (one
+ * all_gather of these records over NCCL, then bogp_reduce_results) -- no host round trip per rank.            */
+typedef struct bogp_result {
+    double  score;        /* best acquisition value, -inf if no candidate was scored                          */
+    int64_t index;        /* its global flat index (INT64_MAX if none)                                         */
+    int32_t nan_flag;     /* 1 if any acquisition value was NaN (reference: IndexError, point_selector.py:207) */
+    int32_t reserved;
+} bogp_result;
+
 size_t bogp_acquire_workspace_bytes(const bogp_fit* fit, int64_t max_chunk);
 int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand,
                  int64_t c_begin, int64_t c_end, int kind, double explore, double f_best,
@@ -135,11 +156,26 @@ int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand
                  void* d_workspace, size_t workspace_bytes,
                  double* h_best_score, int64_t* h_best_index);
 
+/* The same sweep without any host synchronisation: the winner is left in the caller's device record. */
+int bogp_acquire_async(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candidates* cand,
+                       int64_t c_begin, int64_t c_end, int kind, double explore, double f_best,
+                       double prior_diag, double* d_mu_out, double* d_sigma_out, double* d_acq_out,
+                       void* d_workspace, size_t workspace_bytes, bogp_result* d_result);
+/* Fold `count` device records (several sweeps, or the all_gather of every rank's record) into one with the
+ * reference's tie rule (largest score, then smallest flat index); d_out may be NULL (internal scratch).  With
+ * host pointers given it synchronises and returns the winner (BOGP_ERR_NAN_SCORE if any record carries the flag). */
+int bogp_reduce_results(bogp_ctx* ctx, const bogp_result* d_results, int count, bogp_result* d_out,
+                        double* h_best_score, int64_t* h_best_index);
+
 /* acquisition + arg-max only, on mu/sigma already on the device
  * (lower_confidence_bound(), point_selector.py:197-207).                                */
 int bogp_score_argmax(bogp_ctx* ctx, const double* d_mu, const double* d_sigma, int64_t c,
                       int kind, double explore, double f_best, double* d_acq_out,
                       double* h_best_score, int64_t* h_best_index);
+
+/* same, asynchronous, with the flat index of element 0 given (a shard of a larger candidate set) */
+int bogp_score_argmax_async(bogp_ctx* ctx, const double* d_mu, const double* d_sigma, int64_t c, int64_t index_offset,
+                            int kind, double explore, double f_best, double* d_acq_out, bogp_result* d_result);
 
 /* ---- K3: batched negative log marginal likelihood (+ gradient) -- point_selector.py:111-138
  * R length-scale vectors d_ell[R x dim] against the same (X, y).  nlml_out[R];
@@ -148,6 +184,46 @@ size_t bogp_nlml_batched_workspace_bytes(int64_t n, int dim, int64_t r, int want
 int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int dim,
                       const double* d_ell, int64_t r, double jitter, double* d_nlml_out,
                       double* d_grad_out, void* d_workspace, size_t workspace_bytes);
+
+/* ==== Host-buffer "session" API: what the reference-facing PointSelector binds ====================================
+ * Every pointer below is a HOST pointer (pageable memory is fine): the arrays the reference's methods work on.  A session
+ * owns one context, streams and grow-only device buffers per device; with several devices it shards candidates
+ * (contiguous flat-index slices) and restarts over them from the caller's single thread and reduces the winners with
+ * the reference's tie rule.  Calls return when the host outputs are complete.                                        */
+typedef struct bogp_session bogp_session;
+typedef struct bogp_host_candidates {
+    const double*  h_points;      /* explicit: c_total x dim row-major (predicted_pts, select_parameters.py:279), or NULL  */
+    const double*  h_axes;        /* grid: the dim axes back to back (select_parameters.py:273-274)                        */
+    const int32_t* h_axis_len;    /* grid: dim lengths                                                                      */
+    int64_t        c_total;
+    double         cross_jitter;  /* see bogp_candidates                                                                    */
+} bogp_host_candidates;
+
+int  bogp_session_create(const int* devices, int n_devices, bogp_session** out);   /* n_devices == 0: device 0           */
+void bogp_session_destroy(bogp_session* s);
+int  bogp_session_device_count(const bogp_session* s);
+bogp_ctx* bogp_session_ctx(bogp_session* s, int i);                                 /* context of the i-th device        */
+int64_t bogp_session_launch_count(const bogp_session* s);
+int  bogp_session_set_acquire_path(bogp_session* s, int path);
+/* kernel_rbf(x1, x2) with host arrays                                                     point_selector.py:166-195 */
+int  bogp_session_kernel_matrix(bogp_session* s, const double* h_a, int64_t na, const double* h_b, int64_t nb, int dim,
+                                const double* h_ell, double jitter, double* h_k_out);
+/* The table of tune_kernel: nlml (and optionally its gradient) of r length-scale vectors h_ells[r x dim]; restarts are
+ * dealt to the devices in contiguous blocks and chunked to the free device memory.        point_selector.py:104-163 */
+int  bogp_session_nlml(bogp_session* s, const double* h_x, const double* h_y, int64_t n, int dim, const double* h_ells,
+                       int64_t r, double jitter, double* h_nlml_out, double* h_grad_out);
+/* update_surrogate: K = k(X,X) + jitter I, Cholesky, posterior mean / sigma of candidates [c_begin, c_end), the
+ * acquisition `kind` and its first arg-max (GLOBAL flat index) in the same sweep.  Outputs of length c_end - c_begin,
+ * each optional; with none requested the sweep only returns the winner.  h_nlml_out: nlml of this fit.
+ * Errors: BOGP_ERR_NOT_POSDEF (reference: LinAlgError), BOGP_ERR_NAN_SCORE (reference: IndexError).  point_selector.py:42-102 */
+int  bogp_session_update(bogp_session* s, const double* h_x, const double* h_y, int64_t n, int dim, const double* h_ell,
+                         double jitter, const bogp_host_candidates* cand, int64_t c_begin, int64_t c_end, double prior_diag,
+                         int kind, double explore, double f_best, double* h_mu_out, double* h_sigma_out, double* h_acq_out,
+                         double* h_nlml_out, double* h_best_score, int64_t* h_best_index);
+/* lower_confidence_bound(explore) / EI on the mu, sigma the last update left on the device(s) (h_mu == h_sigma == NULL),
+ * or on host arrays given here (the caller changed mean_func / cov_func).  c = number of candidates.  point_selector.py:197-207 */
+int  bogp_session_score(bogp_session* s, const double* h_mu, const double* h_sigma, int64_t c, int kind, double explore,
+                        double f_best, double* h_acq_out, double* h_best_score, int64_t* h_best_index);
 
 #ifdef __cplusplus
 }

@@ -24,189 +24,25 @@ measured value, select_parameters.py:135,259) and the placeholder objective rows
 """
 from __future__ import annotations
 
-import builtins
-import contextlib
-import io
-import json
 import os
-import runpy
-import shutil
-import sys
-import tempfile
 
 import numpy as np
 
 from . import reference_loader as rl
+from .workflow import NAMES, run_workflow
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tests", "golden", "closed_loop.npz")
-HARD = "/home/hunt-stokes/bayesian_optimisation"
-NAMES = ["T1", "T2", "T3", "T4", "TR", "A1", "A2", "A3", "A4"]
-TRUE = dict(T1=4.9, T2=22.0, T3=110.0, T4=380.0, TR=0.85, A1=0.62, A2=0.28, A3=0.07, A4=0.03)
 
 
-def emission_hist(p):
-    """P(t) = sum_i A_i (exp(-t/t_i) - exp(-t/t_r)) / (t_i - t_r), binned on np.arange(-5, 250, 1)
-    (docs/README.md:20; binning of time_residuals.py:130-132)."""
-    edges = np.arange(-5, 250, 1.0)
-    t = 0.5 * (edges[:-1] + edges[1:])
-    pdf = np.zeros_like(t)
-    for a, ti in zip([p["A1"], p["A2"], p["A3"], p["A4"]], [p["T1"], p["T2"], p["T3"], p["T4"]]):
-        pdf += a * (np.exp(-np.maximum(t, 0) / ti) - np.exp(-np.maximum(t, 0) / p["TR"])) / (ti - p["TR"])
-    pdf[t < 0] = 0.0
-    return pdf
+def main(max_calls=400, sizes=(1, 1, 20)):
+    """sizes: one full algorithm iteration with the deployment's 20-iteration sample loops (run_algo.py:9) for all five
+    parameter groups: 100 PointSelector calls, M = 1 .. 21."""
+    run = run_workflow(rl.load_reference_class(), sizes=sizes, max_calls=max_calls)
+    rec_calls, objectives, events, final = run["calls"], run["objectives"], run["events"], run["final"]
 
-
-def synthetic_objective(p, n_events=3.0e5):
-    """sum (data - MC)^2 with MC normalised to data (time_residuals.py:138-142); O(1e7..1e9)."""
-    data = emission_hist(TRUE) * n_events
-    mc = emission_hist(p)
-    mc = mc * data.sum() / mc.sum()
-    return float(np.sum((data - mc) ** 2))
-
-
-class Recorder:
-    def __init__(self):
-        self.calls = []
-
-
-def make_recording_class(ref_cls, rec):
-    class PointSelector(ref_cls):                      # same name: select_parameters.py:1 imports it
-        def update_surrogate(self):
-            self._rec = dict(X=np.array(self.measured_pts, dtype=np.float64),
-                             y=np.array(self.measured_vals, dtype=np.float64),
-                             P=np.array(self.predicted_pts, dtype=np.float64),
-                             fd=np.array(self.feature_domain),
-                             ls=[np.array(a, dtype=np.float64) for a in
-                                 (self.length_scales if len(self.length_scales) == 2 else [self.length_scales])])
-            super().update_surrogate()
-
-        def lower_confidence_bound(self, explore=4):
-            idx = super().lower_confidence_bound(explore)
-            r = self._rec
-            r.update(kp=np.array(self.kernel_params, dtype=np.float64), index=np.array(idx),
-                     acq_max=float(np.amax(self.acq_func_eval)), mu_min=float(np.amin(self.mean_func)),
-                     sig_max=float(np.amax(self.cov_func)))
-            rec.calls.append(r)
-            return idx
-    return PointSelector
-
-
-@contextlib.contextmanager
-def sandbox(scratch):
-    real_open = builtins.open
-
-    def remap(path):
-        if isinstance(path, str) and path.startswith(HARD):
-            return scratch + path[len(HARD):]
-        return path
-
-    def fake_open(file, *a, **k):
-        return real_open(remap(file), *a, **k)
-
-    cwd = os.getcwd()
-    builtins.open = fake_open
-    os.chdir(scratch)
-    try:
-        yield
-    finally:
-        builtins.open = real_open
-        os.chdir(cwd)
-
-
-def run_script(name):
-    """Run an unmodified reference script; returns its exit code (0 if it falls off the end)."""
-    buf = io.StringIO()
-    try:
-        with contextlib.redirect_stdout(buf):
-            runpy.run_path(os.path.join(rl.REFERENCE_DIR, name), run_name="__main__")
-    except SystemExit as e:
-        return int(e.code or 0)
-    return 0
-
-
-def write_back_objective(scratch):
-    """time_residuals.py:166-182 (block-best update) and :204-217 (objective into the last row)."""
-    with open(os.path.join(scratch, "opto_log.JSON")) as f:
-        log = json.load(f)
-    objective = synthetic_objective(log["parameters"])
-    if objective < log["iteration_info"]["current_block"]["block_best_params"]["obj"]:
-        log["parameters"]["obj"] = objective
-        log["iteration_info"]["current_block"]["block_best_params"] = log["parameters"]
-        with open(os.path.join(scratch, "opto_log.JSON"), "w") as f:
-            json.dump(log, f, indent=4)
-    cur = log["iteration_info"]["current_block"]["param_sampling"]["current_parameters"]
-    algo_iter = log["iteration_info"]["full_algo_iter"]
-    block_iter = log["iteration_info"]["current_block"]["iteration"]
-    if len(cur) == 2 and cur[0] in (0, 2):
-        fname = f"measured_points/{NAMES[cur[0]]}_{NAMES[cur[1]]}_ALGO_{algo_iter}_BLOCK_{block_iter}.npy"
-        col = 2
-    else:
-        fname = f"measured_points/{NAMES[cur[0]]}_ALGO_{algo_iter}_BLOCK_{block_iter}.npy"
-        col = 1
-    path = os.path.join(scratch, fname)
-    if os.path.isfile(path):
-        vals = np.load(path)
-        vals[-1, col] = objective
-        np.save(path, vals)
-    return objective
-
-
-def main(max_calls=400):
-    ref_cls = rl.load_reference_class()
-    rec = Recorder()
-    import types
-    mod = types.ModuleType("point_selector")
-    mod.PointSelector = make_recording_class(ref_cls, rec)
-    sys.modules["point_selector"] = mod
-    rl.install_plot_stubs()
-
-    scratch = tempfile.mkdtemp(prefix="closed_loop_", dir=os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None)
-    for d in ("macros", "measured_points", "plots", "submit_files"):
-        os.makedirs(os.path.join(scratch, d))
-    shutil.copy(os.path.join(rl.REFERENCE_DIR, "bi214_template.mac"), scratch)
-    with open(os.path.join(rl.REFERENCE_DIR, "opto_log.JSON")) as f:
-        info = json.load(f)
-    # shorter loops than the deployment (run_algo.py:7-9 uses 2 / 1 / 20) to keep the trace small
-    info["iteration_info"]["max_iter"] = 1
-    info["iteration_info"]["current_block"]["max_iter"] = 1
-    info["iteration_info"]["current_block"]["param_sampling"]["max_iter"] = 7
-    with open(os.path.join(scratch, "opto_log.JSON"), "w") as f:
-        json.dump(info, f, indent=4)
-
-    objectives, events = [], []
-    np.random.seed(12345)                      # first-ever point is random (select_parameters.py:219)
-
-    def opto_node():
-        while len(rec.calls) < max_calls:
-            rc = run_script("select_parameters.py")
-            assert rc == 0
-            objectives.append(write_back_objective(scratch))
-            if run_script("terminate_opto.py") == 0:
-                return
-
-    def block(two_stage):
-        while len(rec.calls) < max_calls:
-            opto_node()
-            if two_stage:
-                opto_node()
-            rc = run_script("terminate_block.py")
-            events.append(("block", rc))
-            if rc == 0:
-                return
-
-    with sandbox(scratch):
-        while len(rec.calls) < max_calls:
-            block(True)       # FIRST_PAIR : T1,T2 then A1(,A2)
-            block(True)       # SECOND_PAIR: T3,T4 then A3(,A4)
-            block(False)      # RISE_TIME  : TR
-            rc = run_script("terminate_algo.py")
-            events.append(("algo", rc))
-            if rc == 0:
-                break
-        with open(os.path.join(scratch, "opto_log.JSON")) as f:
-            final = json.load(f)
-    shutil.rmtree(scratch, ignore_errors=True)
+    class rec:
+        calls = rec_calls
 
     # pack: variable-length arrays are concatenated with offsets
     n = len(rec.calls)
@@ -241,6 +77,12 @@ def main(max_calls=400):
     for k in ("acq_max", "mu_min", "sig_max"):
         out[k] = np.array([c[k] for c in rec.calls])
     np.savez_compressed(OUT, **out)
+    # every file the reference-class run left behind, for the byte-for-byte diff of tests/test_closed_loop_dropin.py
+    names = sorted(run["files"])
+    blob = b"".join(run["files"][k] for k in names)
+    np.savez_compressed(OUT.replace("closed_loop.npz", "closed_loop_files.npz"), names=np.array(names),
+                        sizes=np.array([len(run["files"][k]) for k in names]), blob=np.frombuffer(blob, dtype=np.uint8),
+                        sizes_arg=np.array(sizes), seed=np.int64(12345))
     print(f"{n} PointSelector calls recorded; M range {out['M'].min()}..{out['M'].max()}; events {events}")
     print("final parameters", dict(zip(NAMES, out["final_parameters"])))
 

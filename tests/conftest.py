@@ -65,3 +65,28 @@ def load_closed_loop():
                           index=g["index"][c][:d], acq_max=float(g["acq_max"][c]), mu_min=float(g["mu_min"][c]),
                           sig_max=float(g["sig_max"][c])))
     return calls
+
+
+# ---------------------------------------------------------------------------------------------
+# achieved parity errors: every GPU parity test reports the largest error it saw, the session prints the
+# table and writes it to gpurun_out/parity_errors.json (copied to profiles/ by hand once per round)
+# ---------------------------------------------------------------------------------------------
+_ERRORS = []
+
+
+def record_error(test, quantity, value, bound=None, note=""):
+    _ERRORS.append({"test": test, "quantity": quantity, "value": float(value), "bound": None if bound is None else float(bound), "note": note})
+    print(f"[parity] {test}: {quantity} = {float(value):.3e}" + (f" (bound {float(bound):.3e})" if bound is not None else "") + (f" {note}" if note else ""))
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _ERRORS:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_errors.json"), "w") as f:
+            json.dump(_ERRORS, f, indent=1)
+    except OSError:
+        pass

@@ -23,10 +23,11 @@ def acquire_path(request):
     global _ENGINE
     if _ENGINE is None:
         _ENGINE = e.GPEngine(0)
+    from bayesian_optimisation_b200 import session as sm
     _ENGINE.set_acquire_path(request.param)
-    e.default_engine().set_acquire_path(request.param)
+    sm.default_session().set_acquire_path(request.param)       # the PointSelector drop-in goes through the host-buffer session
     yield request.param
-    e.default_engine().set_acquire_path("i8")
+    sm.default_session().set_acquire_path("i8")
 
 
 @pytest.fixture
