@@ -62,6 +62,9 @@ SIGNATURES = {
     "bogp_launch_count": (_i64, [_vp]),
     "bogp_set_acquire_path": (_i32, [_vp, _i32]),
     "bogp_get_acquire_path": (_i32, [_vp]),
+    "bogp_set_screening": (_i32, [_vp, _i32]),
+    "bogp_get_screening": (_i32, [_vp]),
+    "bogp_screen_stats": (_i32, [_vp, _pi64, _pi64, _i32]),
     "bogp_profile": (_i32, [_vp, _i32]),
     "bogp_profile_read": (_i32, [_vp, _i32, C.POINTER(_dbl), C.POINTER(_i64)]),
     "bogp_measure_peak": (_i32, [_vp, _i32, _dbl, C.POINTER(_dbl), C.POINTER(_dbl)]),

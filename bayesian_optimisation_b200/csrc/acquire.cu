@@ -221,6 +221,7 @@ struct FinalArgs {
     double* mu_out; double* sigma_out; double* acq_out;   // already offset to this chunk (or null)
     double* block_score; long long* block_index; int* nan_flag;
     int64_t c0, cur, S; int nIq, nImu; int kind; double explore, f_best, prior;
+    const int* d_count; const long long* idx_map;   // screened sweeps: compacted survivors (count on the device, global flat index per slot)
 };
 
 __device__ __forceinline__ double acquisition_value(int kind, double mu, double sigma, double explore, double f_best) {
@@ -249,18 +250,21 @@ __device__ __forceinline__ void block_argmax(double s, long long i, double* bloc
 }
 
 constexpr long long kNoIndex = 0x7fffffffffffffffLL;
+constexpr int kScreenSeed = 4096;          // candidates of the strided seed sample of a screened sweep
 
 __global__ void __launch_bounds__(256) finalize_kernel(FinalArgs f) {
     const int64_t cl = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double score = -INFINITY; long long idx = kNoIndex;
-    if (cl < f.cur) {
+    int64_t cur = f.cur;
+    if (f.d_count) { const int64_t dc = (int64_t)*f.d_count - f.c0; cur = dc < cur ? dc : cur; }
+    if (cl < cur) {
         double q = 0.0, mu = 0.0;
         for (int b = 0; b < f.nIq; b++) q += f.qpart[(int64_t)b * f.S + cl];
         for (int b = 0; b < f.nImu; b++) mu += f.mupart[(int64_t)b * f.S + cl];
         const double var = f.prior - q;
         const double sigma = sqrt(fabs(var));                   // np.sqrt(np.abs(.)), point_selector.py:98
         score = acquisition_value(f.kind, mu, sigma, f.explore, f.f_best);
-        idx = f.c0 + cl;
+        idx = f.idx_map ? f.idx_map[f.c0 + cl] : f.c0 + cl;
         if (f.mu_out) f.mu_out[cl] = mu;
         if (f.sigma_out) f.sigma_out[cl] = sigma;
         if (f.acq_out) f.acq_out[cl] = score;
@@ -300,6 +304,72 @@ __global__ void __launch_bounds__(256) merge_kernel(const double* block_score, c
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; w++) if (better(ws[w], wi[w], s, i)) { s = ws[w]; i = wi[w]; }
         if (better(s, i, best[0], besti[0])) { best[0] = s; besti[0] = i; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arg-max-only sweeps: screen, then score exactly.
+//
+// Both acquisitions are non-decreasing in sigma (LCB = explore*sigma - mu with explore >= 0; dEI/dsigma = phi(z) > 0),
+// and sigma^2 = prior - |L^-1 k_*|^2 <= prior.  So  U(c) = A(mu_c, sqrt(prior))  is an upper bound of candidate c's
+// score that needs only the posterior MEAN (N flops, the mu-only pass of the panel kernel) and not the N^2-flop
+// product.  A candidate with U(c) < best -- `best` being the EXACT score of some candidate already scored -- can
+// neither be the maximum nor tie with it and is dropped; everything else (NaNs included: the comparison is false) is
+// compacted and goes through the exact kernels.  The winner (score, index) is therefore exactly the one of the full
+// sweep.  LCB: the bound is computed with the very operations of the exact score (fl is monotone), no slack.  EI: the
+// computed value of the smooth formula can deviate from monotonicity by rounding, so 1e-12 (|f_best - mu| + sigma_max)
+// -- four orders of magnitude above the rounding error of the two products -- is added to the bound.
+// ------------------------------------------------------------------------------------------------
+struct ScreenArgs {
+    const double* mupart; int nImu; int64_t S;
+    CandDesc cand; int dim;
+    int64_t c0, cur, stride;      // flat indices c0 + i * stride, i < cur
+    int seed;                     // 1: keep every candidate without testing (the strided seed sample)
+    int kind; double explore, f_best, sigma_max;
+    const bogp_result* best;
+    long long* surv_idx; double* surv_pts; int* count; int capacity;
+    unsigned long long* stats;    // [0] candidates screened, [1] survivors (bogp_screen_stats)
+};
+
+__global__ void __launch_bounds__(256) screen_kernel(ScreenArgs a) {
+    const int64_t cl = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool keep = false;
+    long long idx = 0;
+    if (cl < a.cur) {
+        idx = a.c0 + cl * a.stride;
+        keep = true;
+        if (!a.seed) {
+            double mu = 0.0;
+            for (int b = 0; b < a.nImu; b++) mu += a.mupart[(int64_t)b * a.S + cl];      // same order as finalize_kernel
+            double bound = acquisition_value(a.kind, mu, a.sigma_max, a.explore, a.f_best);
+            if (a.kind == BOGP_ACQ_EI) bound += 1e-12 * (fabs(a.f_best - mu) + a.sigma_max);
+            keep = !(bound < a.best->score);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!a.seed) {
+        const unsigned inrange = __ballot_sync(0xffffffffu, cl < a.cur);
+        if (lane == 0 && inrange) { atomicAdd(&a.stats[0], (unsigned long long)__popc(inrange)); if (m) atomicAdd(&a.stats[1], (unsigned long long)__popc(m)); }
+    }
+    if (m == 0u) return;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(a.count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (!keep) return;
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (pos >= a.capacity) return;                      // cannot happen (capacity = batch size); guards the buffers
+    a.surv_idx[pos] = idx;
+    double* dst = a.surv_pts + (int64_t)pos * a.dim;
+    if (a.cand.points) {
+        for (int k = 0; k < a.dim; k++) dst[k] = a.cand.points[idx * a.dim + k];
+    } else {
+        long long f = idx;
+        for (int k = a.dim - 1; k >= 0; k--) {
+            const long long q = f / a.cand.len[k];
+            dst[k] = a.cand.axes[a.cand.off[k] + (int)(f - q * a.cand.len[k])];
+            f = q;
+        }
     }
 }
 
@@ -411,18 +481,69 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         const int prc = fit_ensure_packed(ctx, fit, use_i8 ? BOGP_PATH_INT8_TCGEN05 : BOGP_PATH_FP64_DMMA);
         if (prc) return prc;
     }
-    auto finish_chunk = [&](int64_t c0, int64_t cur, int64_t Sb, const double* qp, const double* mp, int nIq) -> int {
+    auto finish_chunk = [&](int64_t c0, int64_t cur, int64_t Sb, const double* qp, const double* mp, int nIq,
+                            const int* d_count = nullptr, const long long* idx_map = nullptr) -> int {
         const int nfb = (int)((cur + 255) / 256);
         if (nfb > kMaxReduceBlocks) { set_error("bogp_acquire: chunk of %lld candidates exceeds the reducer capacity", (long long)cur); return BOGP_ERR_BAD_ARG; }
         const int64_t o = c0 - c_begin;
         FinalArgs fa{qp, mp, d_mu_out ? d_mu_out + o : nullptr, d_sigma_out ? d_sigma_out + o : nullptr,
                      d_acq_out ? d_acq_out + o : nullptr, ctx->d_block_score, ctx->d_block_index, nan_flag,
-                     c0, cur, Sb, nIq, nI, kind, explore, f_best, prior_diag};
+                     c0, cur, Sb, nIq, nI, kind, explore, f_best, prior_diag, d_count, idx_map};
         BOGP_PROFILED(ctx, BOGP_PROF_FINALIZE, (finalize_kernel<<<nfb, 256, 0, st>>>(fa))); BOGP_LAUNCH_CHECK(ctx);
         BOGP_PROFILED(ctx, BOGP_PROF_MERGE, (merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti))); BOGP_LAUNCH_CHECK(ctx);
         return BOGP_OK;
     };
-    if (use_i8) {
+    const bool want_out = d_mu_out || d_sigma_out || d_acq_out;
+    const bool screen = use_i8 && ctx->screening && !want_out && !ctx->profile && cand->cross_jitter == 0.0 && prior_diag >= 1.0 &&
+                        (kind == BOGP_ACQ_EI || explore >= 0.0) && (c_end - c_begin) >= 4 * kScreenSeed && S >= kScreenSeed;
+    if (screen) {
+        // One buffer set of S candidates.  The tail of the panel region (the digits take 7 of its 8 bytes per entry)
+        // holds the compacted survivors: coordinates, global flat indices and the device-side count.
+        const AcqLayout lb = acq_layout(n_pad, S);
+        char* tail = base + lb.panel + (size_t)n_pad * S * 7;
+        double* surv_pts = reinterpret_cast<double*>(tail);
+        long long* surv_idx = reinterpret_cast<long long*>(tail + (size_t)S * BOGP_MAX_DIM * 8);
+        int* count = reinterpret_cast<int*>(tail + (size_t)S * (BOGP_MAX_DIM + 1) * 8);
+        const int64_t total = c_end - c_begin;
+        auto make_chunk = [&](int64_t c0, int64_t cur_cap, bool compacted) {
+            AcqChunk a{};
+            a.points = compacted ? surv_pts : cd.points; a.axes = compacted ? nullptr : cd.axes; a.cross_jitter = 0.0;
+            for (int k = 0; k < BOGP_MAX_DIM; k++) { a.len[k] = cd.len[k]; a.off[k] = cd.off[k]; }
+            a.x_pad = fit_xpad(fit); a.inv_ell2 = fit_inv_ell2(fit); a.alpha = fit_alpha(fit);
+            a.wp = fit_wp(fit); a.wq = fit_wq(fit); a.wscale = fit_wscale(fit);
+            a.panel = base + lb.panel; a.qpart = (double*)(base + lb.qpart); a.mupart = (double*)(base + lb.mupart);
+            a.c0 = compacted ? 0 : c0; a.c_end = compacted ? cur_cap : c_end; a.cur = cur_cap; a.S = S;
+            a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
+            a.d_count = compacted ? count : nullptr;
+            return a;
+        };
+        auto exact_pass = [&](int64_t cap) -> int {          // the survivors in surv_pts[0 .. *count), at most `cap`
+            const AcqChunk a = make_chunk(0, cap, true);
+            int rc = launch_panel_i8(ctx, a, st); if (rc) return rc;
+            rc = launch_trigemm_i8(ctx, a, st); if (rc) return rc;
+            return finish_chunk(0, cap, S, a.qpart, a.mupart, (int)(n_pad / 128), count, surv_idx);
+        };
+        ScreenArgs sa{};
+        sa.mupart = (double*)(base + lb.mupart); sa.nImu = nI; sa.S = S; sa.cand = cd; sa.dim = dim;
+        sa.kind = kind; sa.explore = explore; sa.f_best = f_best; sa.sigma_max = sqrt(prior_diag);
+        sa.best = d_result; sa.surv_idx = surv_idx; sa.surv_pts = surv_pts; sa.count = count; sa.capacity = (int)S;
+        sa.stats = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 16);
+        // seed: a strided sample over the whole range is scored first, so that the running best is already high
+        // when the first batch is screened
+        BOGP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
+        sa.seed = 1; sa.c0 = c_begin; sa.cur = kScreenSeed; sa.stride = total / kScreenSeed;
+        screen_kernel<<<(unsigned)((sa.cur + 255) / 256), 256, 0, st>>>(sa); BOGP_LAUNCH_CHECK(ctx);
+        int rc = exact_pass(kScreenSeed); if (rc) return rc;
+        sa.seed = 0; sa.stride = 1;
+        for (int64_t c0 = c_begin; c0 < c_end; c0 += S) {
+            const int64_t cur = (c_end - c0 < S) ? (c_end - c0) : S;
+            rc = launch_panel_i8(ctx, make_chunk(c0, cur, false), st, /*mu_only=*/true); if (rc) return rc;
+            BOGP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
+            sa.c0 = c0; sa.cur = cur;
+            screen_kernel<<<(unsigned)((cur + 255) / 256), 256, 0, st>>>(sa); BOGP_LAUNCH_CHECK(ctx);
+            rc = exact_pass((cur + kAcqBN - 1) / kAcqBN * kAcqBN); if (rc) return rc;
+        }
+    } else if (use_i8) {
         // INT8 path.  The panel kernel (FP64/INT pipes) and the tensor-core kernel use different
         // pipes and fit on one SM together, so with two buffer sets the panel of chunk s+1 is built
         // on a second stream while chunk s is on the tensor cores.
@@ -523,6 +644,17 @@ extern "C" int bogp_acquire(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candi
     if (rc) return rc;
     if (!h_best_score && !h_best_index) return BOGP_OK;
     return read_result(ctx, slot, "bogp_acquire", h_best_score, h_best_index);
+}
+
+extern "C" int bogp_screen_stats(bogp_ctx* ctx, int64_t* h_screened, int64_t* h_survived, int reset) {
+    if (!ctx) { set_error("bogp_screen_stats: null context"); return BOGP_ERR_BAD_ARG; }
+    unsigned long long h[2] = {0, 0};
+    BOGP_CUDA_CHECK(cudaMemcpyAsync(h, ctx->d_scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) BOGP_CUDA_CHECK(cudaMemsetAsync(ctx->d_scalars + 16, 0, sizeof(h), ctx->stream));
+    BOGP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (h_screened) *h_screened = (int64_t)h[0];
+    if (h_survived) *h_survived = (int64_t)h[1];
+    return BOGP_OK;
 }
 
 extern "C" int bogp_reduce_results(bogp_ctx* ctx, const bogp_result* d_results, int count, bogp_result* d_out,

@@ -111,6 +111,7 @@ struct PanelI8Args {
     uint8_t* panel; double* mupart;
     int64_t c0, c_end, S;
     int n, n_pad, dim;
+    const int* d_count;       // screened sweeps: number of valid candidates of the (compacted) array lives on the device
 };
 
 // 4x4 byte transpose: out[m] = (byte m of w0, byte m of w1, byte m of w2, byte m of w3)
@@ -158,13 +159,27 @@ struct PanelRowCtx {
     int nvr, jq, nl, tid; double jit;
 };
 
-template <int DIMP, bool UB, int T>
+// MUONLY: the screening pass of an arg-max-only sweep -- the same k_* values and the same partial posterior means
+// (same operations, same order: bit-identical mu), but no digits are formed or stored.
+template <int DIMP, bool UB, int T, bool MUONLY>
 __device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double (&pc)[DIMP], const double (&il)[DIMP]) {
     double mu = 0.0;      // this thread's 4 row groups, ascending
     // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
     for (int g = c.tid >> 6; g < kAcqBM / 16; g += 4) {
         uint32_t pk[kI8Slices][4];
         double mug = 0.0;
+        if (MUONLY) {
+#pragma unroll 4
+            for (int e = 0; e < 16; e++) {
+                const int jl = g * 16 + e;
+                double v = kstar_row<DIMP, T>(T < DIMP ? c.pre[jl] : 0.0, pc, il, c.xs + jl * DIMP, c.etab);
+                v = jl < c.nvr ? v : 0.0;
+                if (jl == c.jq) v += c.jit;
+                mug += c.al[jl] * v;
+            }
+            mu += mug;
+            continue;
+        }
         if (UB) {
 #pragma unroll
             for (int e4 = 0; e4 < 4; e4++) {
@@ -211,7 +226,7 @@ __device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double 
     return mu;
 }
 
-template <int DIMP, bool UB>
+template <int DIMP, bool UB, bool MUONLY>
 __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     static_assert(DIMP % 2 == 0, "rows of the x block are read as double2");
     __shared__ __align__(128) double ps_raw[kI8BN * BOGP_MAX_DIM];
@@ -228,7 +243,10 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     const int64_t cbase = p.c0 + (int64_t)ct * kI8BN;
     const int dim = p.dim;
     const bool explicit_mode = p.cand.points != nullptr;
-    const int64_t remain = p.c_end - cbase;
+    int64_t c_end = p.c_end;
+    if (p.d_count) { const int64_t dc = *p.d_count; c_end = dc < c_end ? dc : c_end; }
+    const int64_t remain = c_end - cbase;
+    if (remain <= 0) return;                       // tile beyond the device-side count (uniform for the CTA)
     const int nvalid = remain >= kI8BN ? kI8BN : (int)remain;
     bool used_tma = false;
     if (explicit_mode) {
@@ -299,10 +317,10 @@ __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
     rc.jq = (p.cand.cross_jitter != 0.0 && jq64 >= 0 && jq64 < kAcqBM) ? (int)jq64 : -1;
     rc.jit = p.cand.cross_jitter; rc.nl = nl; rc.tid = tid;
     double mu;
-    if (DIMP > 4 && T == 2)      mu = panel_rows<DIMP, UB, (DIMP > 4 ? 2 : DIMP)>(rc, pc, il);
-    else if (DIMP > 4 && T == 3) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 3 : DIMP)>(rc, pc, il);
-    else if (DIMP > 4 && T == 4) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 4 : DIMP)>(rc, pc, il);
-    else                         mu = panel_rows<DIMP, UB, DIMP>(rc, pc, il);
+    if (DIMP > 4 && T == 2)      mu = panel_rows<DIMP, UB, (DIMP > 4 ? 2 : DIMP), MUONLY>(rc, pc, il);
+    else if (DIMP > 4 && T == 3) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 3 : DIMP), MUONLY>(rc, pc, il);
+    else if (DIMP > 4 && T == 4) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 4 : DIMP), MUONLY>(rc, pc, il);
+    else                         mu = panel_rows<DIMP, UB, DIMP, MUONLY>(rc, pc, il);
     mured[tid >> 6][nl] = mu;
     __syncthreads();
     if (tid < kI8BN) {                              // fixed-order sum of the 4 thread groups
@@ -344,6 +362,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 struct TriI8Args {
     const uint8_t* wq; const uint8_t* panel; const double* wscale; double* qpart;
     int nI, nct, n_pad; int64_t S; int b_signed; int group;   // group = candidate tiles scheduled together (L2 reuse of the panel)
+    const int* d_count; int64_t count_c0;                     // screened sweeps: valid candidates = *d_count - count_c0 (device side)
 };
 
 // int32 (held as raw bits) -> double without the conversion unit: 2^52 + 2^31 + r is exact in the
@@ -371,6 +390,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) trigemm_i8_kernel(TriI8Args g) 
     const int ib = g.nI - 1 - rem / gc;
     const int ct = grp * g.group + rem % gc;
     if (ib < 0) return;                                           // padding CTAs of the last (partial) group
+    if (g.d_count && (int64_t)ct * kI8BN >= (int64_t)*g.d_count - g.count_c0) return;   // candidate tile beyond the device-side count
     const int nk = (ib + 1) * (kI8BM / kI8KB);
     const uint8_t* wsrc = g.wq + (int64_t)ib * (ib + 1) / 2 * (kI8BM / kI8KB) * kI8ATile;
     const uint8_t* psrc = g.panel + (int64_t)ct * (g.n_pad / kI8KB) * kI8BTile;
@@ -516,19 +536,21 @@ int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp,
 
 size_t i8_panel_bytes(int64_t n_pad, int64_t S) { return (size_t)n_pad * S * kI8Slices; }
 
-int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
+int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream, bool mu_only) {
     const int nct = (int)((a.cur + kI8BN - 1) / kI8BN);
     PanelI8Args pa{};
+    pa.d_count = a.d_count;
     pa.cand.points = a.points; pa.cand.axes = a.axes; pa.cand.cross_jitter = a.cross_jitter;
     for (int k = 0; k < BOGP_MAX_DIM; k++) { pa.cand.len[k] = a.len[k]; pa.cand.off[k] = a.off[k]; }
     pa.x_pad = a.x_pad; pa.inv_ell2 = a.inv_ell2; pa.alpha = a.alpha; pa.panel = (uint8_t*)a.panel; pa.mupart = a.mupart;
     pa.c0 = a.c0; pa.c_end = a.c_end; pa.S = a.S; pa.n = a.n; pa.n_pad = a.n_pad; pa.dim = a.dim;
     const bool ub = a.n_pad <= 8192;      // unsigned panel digits while the int32 level sums cannot overflow
     const dim3 pgrid(nct, a.n_pad / kAcqBM);
-#define BOGP_PANEL_I8(D)                                                                                          \
-    do {                                                                                                          \
-        if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true><<<pgrid, 256, 0, stream>>>(pa))); }   \
-        else    { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false><<<pgrid, 256, 0, stream>>>(pa))); }  \
+#define BOGP_PANEL_I8(D)                                                                                                 \
+    do {                                                                                                                 \
+        if (mu_only) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true, true><<<pgrid, 256, 0, stream>>>(pa))); }  \
+        else if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true, false><<<pgrid, 256, 0, stream>>>(pa))); } \
+        else         { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false, false><<<pgrid, 256, 0, stream>>>(pa))); }\
     } while (0)
     if (a.dim <= 2) BOGP_PANEL_I8(2); else if (a.dim <= 4) BOGP_PANEL_I8(4); else if (a.dim <= 6) BOGP_PANEL_I8(6);
     else if (a.dim <= 8) BOGP_PANEL_I8(8); else if (a.dim <= 10) BOGP_PANEL_I8(10); else if (a.dim <= 12) BOGP_PANEL_I8(12);
@@ -549,7 +571,7 @@ int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
     int group = (int)((32u << 20) / ((size_t)(a.n_pad / kI8KB) * kI8BTile));     // ~32 MB of panel per group
     group = group < 1 ? 1 : (group > 64 ? 64 : group);
     const int ngroups = (nct + group - 1) / group;
-    TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S, ub ? 0 : 1, group};
+    TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S, ub ? 0 : 1, group, a.d_count, a.c0};
     BOGP_PROFILED(ctx, BOGP_PROF_TRIGEMM, (trigemm_i8_kernel<<<ngroups * nI * group, kI8Threads, kI8Smem, stream>>>(ta)));
     BOGP_LAUNCH_CHECK(ctx);
     return BOGP_OK;

@@ -50,6 +50,7 @@ extern "C" int bogp_create(int device, bogp_ctx** out) {
         c->acquire_path = (e && (!strcmp(e, "fp64") || !strcmp(e, "dmma") || !strcmp(e, "0"))) ? BOGP_PATH_FP64_DMMA
                         : (e && (!strcmp(e, "i8") || !strcmp(e, "int8") || !strcmp(e, "1"))) ? BOGP_PATH_INT8_TCGEN05 : BOGP_PATH_DEFAULT;
     }
+    c->screening = 1;
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     BOGP_CUDA_CHECK(cudaMalloc(&c->d_block_score, kMaxReduceBlocks * sizeof(double)));
@@ -81,6 +82,13 @@ extern "C" int bogp_set_acquire_path(bogp_ctx* ctx, int path) {
     return BOGP_OK;
 }
 extern "C" int bogp_get_acquire_path(const bogp_ctx* ctx) { return ctx ? ctx->acquire_path : -1; }
+
+extern "C" int bogp_set_screening(bogp_ctx* ctx, int enable) {
+    if (!ctx) { set_error("bogp_set_screening: null context"); return BOGP_ERR_BAD_ARG; }
+    ctx->screening = enable ? 1 : 0;
+    return BOGP_OK;
+}
+extern "C" int bogp_get_screening(const bogp_ctx* ctx) { return ctx ? ctx->screening : -1; }
 
 extern "C" int bogp_profile(bogp_ctx* ctx, int enable) {
     if (!ctx) { set_error("bogp_profile: null context"); return BOGP_ERR_BAD_ARG; }

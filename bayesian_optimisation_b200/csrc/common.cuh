@@ -85,6 +85,7 @@ struct bogp_ctx {
     int64_t      inblock_launches;   // launches of the fused in-block kernel (its grid-barrier counter only grows)
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
+    int          screening;     // arg-max-only sweeps: screen by the posterior-mean bound, score survivors exactly (bogp_set_screening)
     cudaEvent_t  ev[2];
     double       prof_ms[8];
     int64_t      prof_n[8];

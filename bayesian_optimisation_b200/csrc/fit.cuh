@@ -34,8 +34,9 @@ struct AcqChunk {
     void* panel; double* qpart; double* mupart;
     int64_t c0, c_end, cur, S;
     int n, n_pad, dim;
+    const int* d_count;               // screened sweeps: the candidates are a compacted array whose length lives on the device
 };
-int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream);
+int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream, bool mu_only = false);
 int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream);
 size_t i8_wq_bytes(int64_t n_pad);
 size_t i8_panel_bytes(int64_t n_pad, int64_t S);

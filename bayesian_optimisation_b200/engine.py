@@ -163,6 +163,18 @@ class GPEngine:
         code = {"fp64": _lib.PATH_FP64_DMMA, "dmma": _lib.PATH_FP64_DMMA, "i8": _lib.PATH_INT8_TCGEN05, "int8": _lib.PATH_INT8_TCGEN05}[path]
         _lib.check(self.lib.bogp_set_acquire_path(self._ctx, code))
 
+    def set_screening(self, enable: bool):
+        """Arg-max-only sweeps: screen by the posterior-mean bound and score only the survivors exactly (default on;
+        same winner as the full sweep -- include/bogp.h)."""
+        _lib.check(self.lib.bogp_set_screening(self._ctx, 1 if enable else 0))
+
+    def screen_stats(self, reset: bool = True):
+        """(candidates screened, survivors) since the last reset."""
+        a, b = C.c_int64(), C.c_int64()
+        self._sync_stream()
+        _lib.check(self.lib.bogp_screen_stats(self._ctx, C.byref(a), C.byref(b), 1 if reset else 0))
+        return int(a.value), int(b.value)
+
     def profile(self, enable: bool):
         """Per-kernel CUDA-event timing of the acquisition sweep (measurement aid; serialises the stream)."""
         _lib.check(self.lib.bogp_profile(self._ctx, 1 if enable else 0))

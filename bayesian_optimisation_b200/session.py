@@ -81,6 +81,11 @@ class Session:
         code = {"fp64": _lib.PATH_FP64_DMMA, "dmma": _lib.PATH_FP64_DMMA, "i8": _lib.PATH_INT8_TCGEN05, "int8": _lib.PATH_INT8_TCGEN05}[path]
         _lib.check(self.lib.bogp_session_set_acquire_path(self._h, code))
 
+    def set_screening(self, enable: bool):
+        """Screening of arg-max-only sweeps (`update(..., outputs=False)`), per device context (include/bogp.h)."""
+        for i in range(len(self.devices)):
+            _lib.check(self.lib.bogp_set_screening(C.c_void_p(self.lib.bogp_session_ctx(self._h, i)), 1 if enable else 0))
+
     # ------------------------------------------------------------------ point_selector.py:166-195
     def kernel_matrix(self, a, b, ell, jitter: float = 0.0) -> np.ndarray:
         a, b = _f64(a), _f64(b)

@@ -262,7 +262,10 @@ def run_gpu_arm(args):
     #      SM clock, which stays power-capped for a while after a sweep -- it is timed again after them, and THAT is the headline
     fits_before = time_fits(20)
 
-    # ---- device-resident throughput ("value")
+    # ---- device-resident throughput ("value"): every candidate of the slice gets its exact posterior variance and score
+    #      (screening of arg-max-only sweeps, which drops candidates that provably cannot win, is switched OFF here and
+    #      measured separately below)
+    eng.set_screening(False)
     for k in range(args.warmup):
         device_step(k)
     sampler = ClockSampler(local)
@@ -295,6 +298,26 @@ def run_gpu_arm(args):
     a1.record()
     barrier()
     lcb_value = step_total * 2 / (max_over_ranks(a0.elapsed_time(a1)) * 1e-3)
+
+    # ---- the same steps with the screen the library applies by default to arg-max-only sweeps: identical winner, only the
+    #      candidates whose posterior-mean bound reaches the best exact score so far go through the N^2 product
+    eng.set_screening(True)
+    eng.screen_stats()
+    scr_last = device_step(args.warmup)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for k in range(args.steps):
+        scr_last = device_step(args.warmup + k)
+    s1.record()
+    barrier()
+    screened_value = step_total * args.steps / (max_over_ranks(s0.elapsed_time(s1)) * 1e-3)
+    n_scr, n_surv = eng.screen_stats()
+    screened = {"value": screened_value, "unit": UNIT, "survivor_fraction_rank0": (n_surv / n_scr) if n_scr else None,
+                "same_winner_as_full_sweep": bool(scr_last == last),
+                "what": "arg-max-only sweep with the posterior-mean screen (include/bogp.h bogp_set_screening): exact (score, index), "
+                        "the N^2 product only for candidates whose bound A(mu, sqrt(prior)) reaches the running best"}
+    eng.set_screening(False)
 
     # ---- end to end through the reference-facing class: pageable host numpy in, host numpy out.  Under torchrun every
     #      rank hands the WHOLE candidate array of the step to PointSelector, which scores its slice on its GPU, all-gathers
@@ -403,7 +426,7 @@ def run_gpu_arm(args):
                 "candidates_per_step_per_gpu": cands, "candidates_per_step": step_total,
                 "fit_ms": float(np.median(fits_after)), "fit_ms_best": float(min(fits_before + fits_after)),
                 "fit_ms_before_sweeps_median": float(np.median(fits_before)), "fit_ms_after_sweeps_median": float(np.median(fits_after)),
-                "lcb_candidates_per_s": lcb_value,
+                "lcb_candidates_per_s": lcb_value, "argmax_only_screened": screened,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "PointSelector.update_surrogate() + expected_improvement(): pageable host numpy arrays in and out through the "
                                "host-buffer C ABI (bogp_session_*)" + ("; one process per GPU, slices all-gathered, one-record max-loc exchange" if world > 1 else ""),

@@ -66,6 +66,14 @@ int64_t bogp_launch_count(const bogp_ctx* ctx);
 #define BOGP_PATH_DEFAULT       BOGP_PATH_INT8_TCGEN05
 int bogp_set_acquire_path(bogp_ctx* ctx, int path);
 int bogp_get_acquire_path(const bogp_ctx* ctx);
+/* Arg-max-only sweeps (no mu / sigma / acquisition outputs requested) are screened by default: the posterior mean of
+ * every candidate gives an exact upper bound of its score (both acquisitions grow with sigma, and sigma^2 <= prior);
+ * candidates whose bound is below the best exact score so far are dropped, the rest is scored exactly.  The returned
+ * (score, index) is the one of the unscreened sweep (csrc/acquire.cu, screen_kernel).  0 switches it off.          */
+int bogp_set_screening(bogp_ctx* ctx, int enable);
+int bogp_get_screening(const bogp_ctx* ctx);
+/* candidates that went through the screen / that survived it since the last reset (synchronises the stream) */
+int bogp_screen_stats(bogp_ctx* ctx, int64_t* h_screened, int64_t* h_survived, int reset);
 /* Measurement aid: when enabled, each kernel of the acquisition sweep is bracketed by CUDA
  * events on the launching stream (this serialises the stream; never enable it inside a timed
  * region).  kernel_id: 0 panel, 1 tri-GEMM, 2 finalize, 3 merge.                            */

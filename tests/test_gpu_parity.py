@@ -4,12 +4,16 @@ variance and log marginal likelihood within 1e-9 relative in fp64; selected inde
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, record_error
 from oracle import gp_oracle as o
 
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
+# Absolute slack of the sigma^2 comparisons.  Round 1 used max(2e-11, cond*eps); the long-double truth of
+# tests/test_gpu_configs.py shows that this is the ORACLE's error (explicit inverse), not the device's (1e-14 absolute even at
+# cond 4e7), so it is now what the runs actually need: see profiles/r02_parity_errors.json for the achieved values.
+VAR_FLOOR = 2e-12
 
 
 _ENGINE = None
@@ -45,7 +49,12 @@ def assert_var_close(got, want, cond=None, rtol=RTOL):
     (explicit inverse) and this path (Cholesky) carry an ABSOLUTE error ~ cond(K)*eps of the
     prior: 1e-9 relative holds wherever sigma^2 >> cond*eps, and the absolute
     floor below is max(2e-11, cond(K)*eps)."""
-    atol = 2e-11 if cond is None else max(2e-11, cond * np.finfo(np.float64).eps)
+    atol = VAR_FLOOR if cond is None else max(VAR_FLOOR, 0.05 * cond * np.finfo(np.float64).eps)
+    diff = np.abs(np.asarray(got) - np.asarray(want))
+    import inspect
+    who = inspect.stack()[1].function
+    record_error(who, "sigma^2: max abs err vs oracle", diff.max(), atol, note=f"max rel err {(diff / np.maximum(np.abs(want), 1e-300)).max():.2e}, min sigma^2 {np.abs(want).min():.2e}"
+                 + (f", cond {cond:.2g}" if cond else ""))
     np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
 
 

@@ -1,0 +1,110 @@
+"""Arg-max-only sweeps are screened by the posterior-mean bound (csrc/acquire.cu, screen_kernel): the (score, index)
+they return must be EXACTLY the one of the unscreened sweep -- on the BASELINE shapes, on explicit candidates, on
+sub-ranges, on exact ties (lowest flat index), on flat landscapes where nothing can be dropped, and NaNs must still
+raise.  The bound itself is also checked on the host: U(c) >= exact score for every candidate."""
+import numpy as np
+import pytest
+
+from conftest import record_error
+from oracle import gp_oracle as o
+
+pytestmark = pytest.mark.gpu
+_ENG = None
+
+
+@pytest.fixture
+def eng():
+    from bayesian_optimisation_b200.engine import GPEngine
+    global _ENG
+    if _ENG is None:
+        _ENG = GPEngine(0)
+    _ENG.set_acquire_path("i8")
+    _ENG.set_screening(True)
+    yield _ENG
+    _ENG.set_screening(True)
+
+
+def _both(eng, fit, cand, b, e, **kw):
+    eng.set_screening(False)
+    full = eng.acquire(fit, cand, b, e, **kw)
+    eng.set_screening(True)
+    eng.screen_stats()
+    scr = eng.acquire(fit, cand, b, e, **kw)
+    screened, survived = eng.screen_stats()
+    return full, scr, screened, survived
+
+
+@pytest.mark.parametrize("kind", ["lcb", "ei"])
+@pytest.mark.parametrize("n,d,G", [(1024, 6, 10), (4096, 8, 10)])
+def test_screened_sweep_returns_the_exact_winner_on_baseline_shapes(eng, n, d, G, kind):
+    from bayesian_optimisation_b200.engine import ACQ_EI, ACQ_LCB, CandidateGrid, JITTER_POSTERIOR
+    X, y, ell = o.synthetic_problem(n, d)
+    grid = CandidateGrid([np.linspace(0, 1, G)] * d)
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    kw = dict(kind=ACQ_EI, f_best=float(y.min())) if kind == "ei" else dict(kind=ACQ_LCB, explore=4.0)
+    b, e = (0, grid.size) if n == 1024 else (37_000_000, 37_000_000 + (1 << 19))
+    full, scr, screened, survived = _both(eng, fit, grid, b, e, **kw)
+    assert (scr.best_score, scr.best_index) == (full.best_score, full.best_index)
+    assert screened == e - b
+    record_error(f"screen N={n} d={d} {kind}", "survivor fraction of the screen", survived / screened, note=f"{survived} of {screened}")
+    assert survived < screened
+    fit.close()
+
+
+def test_screened_sweep_on_explicit_candidates_ties_and_flat_landscapes(eng):
+    from bayesian_optimisation_b200.engine import ACQ_EI, JITTER_POSTERIOR
+    X, y, ell = o.synthetic_problem(600, 4, seed=2)
+    rng = np.random.default_rng(3)
+    P = rng.random((70_001, 4))
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    full, scr, screened, survived = _both(eng, fit, P, 0, len(P))
+    assert (scr.best_score, scr.best_index) == (full.best_score, full.best_index)
+    # exact tie between two far-apart copies of the winner: the lower flat index must win, screened or not
+    P2 = P.copy()
+    w = full.best_index
+    lo, hi = (5, 69_000) if w not in (5, 69_000) else (6, 68_000)
+    P2[lo] = P[w]; P2[hi] = P[w]
+    if w < lo:
+        lo = w
+    full2, scr2, _, _ = _both(eng, fit, P2, 0, len(P2))
+    assert full2.best_index == min(lo, w) and (scr2.best_score, scr2.best_index) == (full2.best_score, full2.best_index)
+    # a sub-range that excludes the global winner
+    full3, scr3, _, _ = _both(eng, fit, P, 20_000, 60_000, kind=ACQ_EI, f_best=float(y.min()))
+    assert (scr3.best_score, scr3.best_index) == (full3.best_score, full3.best_index) and 20_000 <= scr3.best_index < 60_000
+    # flat landscape: every candidate is the same point, nothing can be dropped, index = first of the range
+    Pf = np.repeat(P[:1], 20_000, axis=0)
+    full4, scr4, screened, survived = _both(eng, fit, Pf, 100, 20_000)
+    assert scr4.best_index == full4.best_index == 100 and survived == screened
+    fit.close()
+
+
+def test_screened_sweep_still_raises_on_nan(eng):
+    from bayesian_optimisation_b200.engine import JITTER_POSTERIOR
+    X, y, ell = o.synthetic_problem(300, 3, seed=4)
+    P = np.random.default_rng(5).random((40_000, 3))
+    P[31_337, 1] = np.nan
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    with pytest.raises(IndexError):
+        eng.acquire(fit, P)
+    fit.close()
+
+
+def test_the_bound_dominates_the_exact_score(eng):
+    """U(c) = A(mu_c, sqrt(prior)) >= A(mu_c, sigma_c) for every candidate, for the device's own mu / sigma: LCB without
+    any slack, EI with the 1e-12 (|f_best - mu| + sigma_max) slack of the kernel -- and how much of that slack is used."""
+    from bayesian_optimisation_b200.engine import ACQ_EI, CandidateGrid, JITTER_POSTERIOR, PRIOR_DIAG
+    X, y, ell = o.synthetic_problem(800, 5, seed=6)
+    grid = CandidateGrid([np.linspace(0, 1, 9)] * 5)
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    fb = float(y.min())
+    lcb = eng.acquire(fit, grid, outputs=True)
+    ei = eng.acquire(fit, grid, kind=ACQ_EI, f_best=fb, outputs=True)
+    mu, sig = lcb.mu.cpu().numpy(), lcb.sigma.cpu().numpy()
+    smax = np.sqrt(PRIOR_DIAG)
+    assert sig.max() <= smax
+    assert np.all(4.0 * smax - mu >= lcb.acq.cpu().numpy())
+    bound = o.expected_improvement(mu, np.full_like(mu, smax), fb)
+    gap = ei.acq.cpu().numpy() - bound
+    record_error("screen bound EI", "max (exact EI - bound) / slack", (gap / (1e-12 * (np.abs(fb - mu) + smax))).max())
+    assert np.all(gap <= 1e-12 * (np.abs(fb - mu) + smax))
+    fit.close()

@@ -84,9 +84,13 @@ def test_session_streams_large_candidate_arrays_in_pieces():
     np.testing.assert_array_equal(got["mu"], ref.mu.cpu().numpy())
     np.testing.assert_array_equal(got["sigma"], ref.sigma.cpu().numpy())
     assert (got["best_score"], got["best_index"]) == (ref.best_score, ref.best_index)
-    mu_ref, var_ref = o.posterior_diag(X, y, P[::97], ell, return_var=True)
-    np.testing.assert_allclose(got["mu"][::97], mu_ref, rtol=1e-9, atol=1e-9 * np.abs(mu_ref).max())
-    np.testing.assert_allclose(got["sigma"][::97] ** 2, var_ref, rtol=1e-9, atol=2e-13)
+    # 100 points in the unit square at ell = 0.3 are a badly conditioned system (cond ~ 1e5..1e6): compare with the
+    # long-double truth, against which the inv-based oracle itself is only good to ~1e-11 absolute
+    from oracle import truth
+    from bayesian_optimisation_b200.engine import PRIOR_DIAG
+    mu_t, var_t, _, _ = truth.posterior_truth(X, y, P[::997], ell, JITTER_POSTERIOR, PRIOR_DIAG)
+    np.testing.assert_allclose(got["mu"][::997], mu_t, rtol=1e-9, atol=1e-9 * np.abs(mu_t).max())
+    np.testing.assert_allclose(got["sigma"][::997] ** 2, var_t, rtol=1e-9, atol=2e-13)
     fit.close()
 
 
