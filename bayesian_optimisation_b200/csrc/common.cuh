@@ -82,7 +82,6 @@ struct bogp_ctx {
     cudaStream_t aux_stream;      // high priority: serial chains / panel builder
     cudaStream_t aux2_stream;     // default priority: work that may fill idle SMs (interleaved triangular inverse)
     cudaEvent_t  ev_fork, ev_panel[2], ev_done[2], ev_aux2;
-    int64_t      inblock_launches;   // launches of the fused in-block kernel (its grid-barrier counter only grows)
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
     int          screening;     // arg-max-only sweeps: screen by the posterior-mean bound, score survivors exactly (bogp_set_screening)

@@ -111,7 +111,7 @@ int trtri_recursive(bogp_ctx* ctx, const double* d_l, int64_t ldl, int64_t strid
 // ------------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky, batch of `batch` matrices (strides in doubles).
 // ------------------------------------------------------------------------------------------------
-static int cholesky_blocked_v1(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
+static int cholesky_blocked_plain(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
                                int64_t strideW, double* d_logdet, int* d_info, int batch) {
     if (n % kDiagNB != 0) { set_error("cholesky: n=%lld is not a multiple of %d", (long long)n, kDiagNB); return BOGP_ERR_BAD_ARG; }
     // Two-level right-looking blocking: an outer panel of kOuter columns is factored with
@@ -166,31 +166,18 @@ static int cholesky_blocked_v1(bogp_ctx* ctx, double* d_a, int64_t n, int64_t ld
 // ------------------------------------------------------------------------------------------------
 // One launch for the whole serial part of a 256-column panel: factor the 256x256 diagonal block
 // (4 diagonal 64-blocks with their small panel solves and updates) and invert its factor (two
-// recursive-doubling levels).  8 CTAs share the tile work of each phase and meet at a software
-// grid barrier (global counter, release/acquire fences); all cross-CTA data is read L2-coherently
-// (cp.async.cg / ld.cg).  This replaces 26 dependent launches per panel by one.
+// recursive-doubling levels).  8 CTAs -- one thread-block cluster -- share the tile work of each phase and
+// meet at the hardware cluster barrier; all cross-CTA data is read L2-coherently (cp.async.cg / ld.cg).
+// This replaces 26 dependent launches per panel by one.
 // ------------------------------------------------------------------------------------------------
 struct InBlockArgs {
     double* a; int64_t lda;      // diagonal block A[ko.., ko..] lives at a + ko*(lda+1)
     double* w; int64_t ldw;
     double* t;                   // scratch, >= 16384 doubles
     double* logdet; int* info;
-    unsigned* counter; unsigned base;   // grid barrier: counter value at kernel start
     int kblk0;                   // first 64-block index of the panel (ko / 64)
 };
 constexpr int kInBlockCtas = 8;
-
-__device__ __forceinline__ void inblock_barrier(unsigned* counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 // Hardware barrier of a thread-block cluster with release/acquire semantics: every global write made by a CTA of
 // the cluster before it arrives is visible to every CTA after the wait (about 0.2 us instead of the 2 us of an
@@ -199,10 +186,7 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// CLUSTER = true: the 8 CTAs are one thread-block cluster (co-scheduled by the hardware, hardware barrier);
-// CLUSTER = false: plain grid with the software barrier above (the CTAs are co-resident because the kernel runs on
-// the high-priority stream and needs only 8 SMs).
-template <bool CLUSTER>
+// The 8 CTAs are ONE thread-block cluster: co-scheduled by the hardware, meeting at the hardware cluster barrier.
 __device__ __forceinline__ void inblock256_body(const InBlockArgs& g) {
     extern __shared__ __align__(16) double smem[];
     DiagSmem& dsm = *reinterpret_cast<DiagSmem*>(smem);
@@ -210,11 +194,7 @@ __device__ __forceinline__ void inblock256_body(const InBlockArgs& g) {
     constexpr int NB = kDiagNB;
     double* A = g.a + (int64_t)g.kblk0 * NB * (g.lda + 1);     // 256 x 256 diagonal block
     double* W = g.w + (int64_t)g.kblk0 * NB * (g.ldw + 1);
-    unsigned target = g.base;
-    auto barrier = [&]() {
-        if (CLUSTER) cluster_barrier();
-        else { target += kInBlockCtas; inblock_barrier(g.counter, target); }
-    };
+    auto barrier = [&]() { cluster_barrier(); };
     auto tile = [&](auto fn) { __syncthreads(); fn(); };          // shared memory is reused between tiles
 
     for (int k = 0; k < 4; k++) {
@@ -278,8 +258,7 @@ __device__ __forceinline__ void inblock256_body(const InBlockArgs& g) {
     }
 }
 
-__global__ void __launch_bounds__(256) inblock256_kernel(InBlockArgs g) { inblock256_body<false>(g); }
-__global__ void __cluster_dims__(kInBlockCtas, 1, 1) __launch_bounds__(256) inblock256_cluster_kernel(InBlockArgs g) { inblock256_body<true>(g); }
+__global__ void __cluster_dims__(kInBlockCtas, 1, 1) __launch_bounds__(256) inblock256_cluster_kernel(InBlockArgs g) { inblock256_body(g); }
 
 // Pipelined variant of the driver below for a single matrix: the serial chain
 //   [factor + invert diagonal block] -> [panel rows of the NEXT diagonal block] -> [update that block]
@@ -315,8 +294,7 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
     // count) are cheaper than 64 read-modify-write passes over the accumulator.
     const int64_t npan = n / kOuter;
     const bool interleave = w_level && n >= 1024 && n % kOuter == 0;
-    static const char* trtri_env = getenv("BOGP_TRTRI");       // experiment switch: "doubling" | "right"
-    const bool want_doubling = trtri_env ? trtri_env[0] == 'd' : n > 4096;     // measured: 4096 4.01 vs 4.42 ms, 8192 21.1 vs 18.6 ms, 16384 142 vs 120 ms
+    const bool want_doubling = n > 4096;     // measured (right-looking vs doubling): 4096 4.01 vs 4.42 ms, 8192 21.1 vs 18.6 ms, 16384 142 vs 120 ms
     const bool doubling = interleave && want_doubling && (npan & (npan - 1)) == 0;
     cudaStream_t ts = ctx->aux2_stream;
     if (interleave && !doubling) {
@@ -372,29 +350,20 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
         return BOGP_OK;
     };
     auto schedule_trtri = [&](int64_t pnl) -> int { return doubling ? schedule_doubling(pnl) : schedule_rightlooking(pnl); };
-    constexpr int kInBlockPhases = 12;                         // barriers per inblock256_kernel launch
     constexpr size_t kInBlockSmem = GemmSmem<64, 64>::bytes > sizeof(DiagSmem) ? GemmSmem<64, 64>::bytes : sizeof(DiagSmem);
-    static const bool fused = !(getenv("BOGP_FIT_FUSED") && getenv("BOGP_FIT_FUSED")[0] == '0');
-    static const bool use_cluster = !(getenv("BOGP_INBLOCK") && getenv("BOGP_INBLOCK")[0] == 's');      // "soft": software barrier
-    unsigned* counter = reinterpret_cast<unsigned*>(ctx->d_flags + 16);
     {
         static DeviceOnce configured;
         if (configured.need(ctx->device)) {
-            BOGP_CUDA_CHECK(cudaFuncSetAttribute(inblock256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInBlockSmem));
             BOGP_CUDA_CHECK(cudaFuncSetAttribute(inblock256_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInBlockSmem));
         }
-        // the barrier counter only grows; restart it long before it can wrap
-        if (ctx->inblock_launches > 30000000) { BOGP_CUDA_CHECK(cudaMemsetAsync(counter, 0, 4, cs)); ctx->inblock_launches = 0; }
     }
     for (int64_t ko = 0; ko < n; ko += kOuter) {
         const int64_t w = (n - ko < kOuter) ? (n - ko) : kOuter;
         double* Add = d_a + ko * (lda + 1);
         double* Wdd = d_w + ko * (ldw + 1);
-        if (w == kOuter && fused) {   // ---- chain: factor and invert the diagonal block, one launch
-            InBlockArgs ia{d_a, lda, d_w, ldw, d_t, d_logdet, d_info, counter, (unsigned)(ctx->inblock_launches * kInBlockPhases * kInBlockCtas), (int)(ko / kDiagNB)};
-            ctx->inblock_launches++;
-            if (use_cluster) inblock256_cluster_kernel<<<kInBlockCtas, 256, kInBlockSmem, cs>>>(ia);
-            else             inblock256_kernel<<<kInBlockCtas, 256, kInBlockSmem, cs>>>(ia);
+        if (w == kOuter) {   // ---- chain: factor and invert the diagonal block, one launch
+            InBlockArgs ia{d_a, lda, d_w, ldw, d_t, d_logdet, d_info, (int)(ko / kDiagNB)};
+            inblock256_cluster_kernel<<<kInBlockCtas, 256, kInBlockSmem, cs>>>(ia);
             BOGP_LAUNCH_CHECK(ctx);
         } else {
             StreamSwap sw(ctx, cs);
@@ -504,7 +473,7 @@ static int cholesky_pipelined(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda
 int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t strideA, double* d_w, int64_t ldw,
                      int64_t strideW, double* d_logdet, int* d_info, int batch, double* d_t, int64_t strideT, int64_t* w_level) {
     if (w_level) *w_level = kDiagNB;
-    if (!d_t) return cholesky_blocked_v1(ctx, d_a, n, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, batch);
+    if (!d_t) return cholesky_blocked_plain(ctx, d_a, n, lda, strideA, d_w, ldw, strideW, d_logdet, d_info, batch);
     {   // same shared-memory carve-out as the GEMMs around it: no SM reconfiguration between the kernels of the chain
         static DeviceOnce configured;
         if (configured.need(ctx->device)) {
@@ -512,20 +481,12 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
         }
     }
     if (n % kDiagNB != 0) { set_error("cholesky: n=%lld is not a multiple of %d", (long long)n, kDiagNB); return BOGP_ERR_BAD_ARG; }
-    {
-        static const bool pipeline = !(getenv("BOGP_FIT_PIPELINE") && getenv("BOGP_FIT_PIPELINE")[0] == '0');
-        if (pipeline && batch == 1 && !ctx->profile && !getenv("BOGP_TRACE_FIT"))
-            return cholesky_pipelined(ctx, d_a, n, lda, d_w, ldw, d_logdet, d_info, d_t, w_level);
-    }
+    if (batch == 1 && !ctx->profile)
+        return cholesky_pipelined(ctx, d_a, n, lda, d_w, ldw, d_logdet, d_info, d_t, w_level);
     constexpr int kOuter = 256;
-    // optional phase trace (BOGP_TRACE_FIT=1): events on the main stream, read back after the loop
-    static const bool trace = getenv("BOGP_TRACE_FIT") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    auto mark = [&]() { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); tev.push_back(e); } };
     for (int64_t ko = 0; ko < n; ko += kOuter) {
         const int64_t wpan = (n - ko < kOuter) ? (n - ko) : kOuter;
         double* Add = d_a + ko * (lda + 1);
-        mark();
         double* Wdd = d_w + ko * (ldw + 1);
         // (a) factor the diagonal block
         for (int64_t ki = 0; ki < wpan; ki += kDiagNB) {
@@ -553,11 +514,9 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
             BOGP_PROFILED(ctx, 6, (rc = launch_gemm<64, 64, A_MK, B_NK, K_ALL>(ctx, s, batch)));
             if (rc) return rc;
         }
-        mark();
         // (b) W_dd = L_dd^-1
         int rc = trtri_recursive(ctx, Add, lda, strideA, Wdd, ldw, strideW, d_t, strideT, wpan, batch, kDiagNB);
         if (rc) return rc;
-        mark();
         const int below = (int)(n - (ko + wpan));
         if (below <= 0) break;
         // (c) tall panel: P = A_below * W_dd^T, in place (a CTA owns 64 complete rows of the panel)
@@ -569,7 +528,6 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
         t.M = below; t.N = (int)wpan; t.K = (int)wpan; t.alpha = 1.0; t.accumulate = 0; t.lower_only = 0;
         BOGP_PROFILED(ctx, 5, (rc = launch_gemm<64, 256, A_MK, B_NK, K_ALL>(ctx, t, batch)));
         if (rc) return rc;
-        mark();
         // (d) trailing update.  With look-ahead (single matrix, not profiling) only the columns of the NEXT
         //     panel are updated on the main stream; the bulk of the SYRK runs on the second stream while the
         //     next panel -- a serial chain that occupies a handful of SMs -- is being factored.
@@ -603,15 +561,6 @@ int cholesky_blocked(bogp_ctx* ctx, double* d_a, int64_t n, int64_t lda, int64_t
             BOGP_CUDA_CHECK(cudaEventRecord(ctx->ev_done[0], ctx->aux_stream));
             if (row1 + kOuter >= n) BOGP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_done[0], 0));   // last bulk: join now
         }
-        mark();
-    }
-    if (trace && tev.size() > 1) {
-        cudaStreamSynchronize(ctx->stream);
-        double ph[5] = {0, 0, 0, 0, 0};
-        for (size_t i = 0; i + 1 < tev.size(); i++) { float ms; cudaEventElapsedTime(&ms, tev[i], tev[i + 1]); ph[i % 5] += ms; }
-        (void)0; fprintf(stderr, "[bogp fit trace n=%lld] diag-block factor %.3f ms, block inverse %.3f ms, tall panel %.3f ms, next-panel update %.3f ms, (gap to next panel) %.3f ms\n",
-                (long long)n, ph[0], ph[1], ph[2], ph[3], ph[4]);
-        for (auto e : tev) cudaEventDestroy(e);
     }
     return BOGP_OK;
 }

@@ -1,7 +1,7 @@
 // Stand-alone timing of the Cholesky diagonal-block kernel variants.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -DBOGP_DIAG_BENCH -I../bayesian_optimisation_b200/csrc -o diag_bench.bin diag_bench.cu
-#define BOGP_DIAG_BENCH
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../bayesian_optimisation_b200/csrc -I. -o diag_bench.bin diag_bench.cu
 #include "chol_diag.cuh"
+#include "diag_variants.cuh"
 #include <vector>
 #include <cmath>
 namespace bogp { void set_error(const char*, ...) {} }
