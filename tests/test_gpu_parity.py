@@ -47,15 +47,31 @@ def _consts():
 def assert_var_close(got, want, cond=None, rtol=RTOL):
     """sigma^2 = 1.000101 - k^T K^-1 k is a cancellation against the prior, so both the reference
     (explicit inverse) and this path (Cholesky) carry an ABSOLUTE error ~ cond(K)*eps of the
-    prior: 1e-9 relative holds wherever sigma^2 >> cond*eps, and the absolute
-    floor below is max(2e-11, cond(K)*eps)."""
-    atol = VAR_FLOOR if cond is None else max(VAR_FLOOR, 0.05 * cond * np.finfo(np.float64).eps)
+    prior.  Against the long-double truth the ORACLE's explicit-inverse arithmetic is off by
+    0.03 .. 0.3 cond*eps (profiles/r02_parity_errors.json) while the device stays at ~1e-14, so where cond(K) is
+    given the slack of the comparison WITH THE ORACLE is max(VAR_FLOOR, 0.5 cond*eps) -- the oracle's own error --
+    and the 1e-9 claim of the device is checked separately against the truth (assert_var_close_to_truth)."""
+    atol = VAR_FLOOR if cond is None else max(VAR_FLOOR, 0.5 * cond * np.finfo(np.float64).eps)
     diff = np.abs(np.asarray(got) - np.asarray(want))
     import inspect
     who = inspect.stack()[1].function
     record_error(who, "sigma^2: max abs err vs oracle", diff.max(), atol, note=f"max rel err {(diff / np.maximum(np.abs(want), 1e-300)).max():.2e}, min sigma^2 {np.abs(want).min():.2e}"
                  + (f", cond {cond:.2g}" if cond else ""))
     np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def assert_var_close_to_truth(got_mu, got_var, X, y, P, ell, jitter, prior, who, max_pts=1500):
+    """Device posterior against the long-double Cholesky truth (oracle/truth_ld.c) on a strided subsample of the
+    candidates: 1e-9 RELATIVE on sigma^2 with no cond-dependent slack (1e-13 absolute only guards sigma^2 -> 0)."""
+    from oracle import truth
+    step = max(1, len(P) // max_pts)
+    sel = np.arange(0, len(P), step)
+    mu_t, var_t, _, _ = truth.posterior_truth(X, y, P[sel], ell, jitter, prior)
+    dv = np.abs(np.asarray(got_var)[sel] - var_t)
+    record_error(who, "sigma^2: max relative err vs long-double truth", (dv / np.abs(var_t)).max(), RTOL,
+                 note=f"max abs err {dv.max():.2e}, min sigma^2 {np.abs(var_t).min():.2e}, {len(sel)} candidates")
+    np.testing.assert_allclose(np.asarray(got_var)[sel], var_t, rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(np.asarray(got_mu)[sel], mu_t, rtol=RTOL, atol=RTOL * np.abs(mu_t).max())
 
 
 def cond_of(X, ell, jitter):
@@ -198,6 +214,7 @@ def test_acquire_grid_matches_oracle(eng, n, d, G, chunk):
     print(f"cond(K) = {cond:.3g}")
     np.testing.assert_allclose(mu, mu_ref, rtol=RTOL, atol=RTOL * np.abs(mu_ref).max())
     assert_var_close(sig ** 2, var_ref, cond)
+    assert_var_close_to_truth(mu, sig ** 2, X, y, P, ell, e.JITTER_POSTERIOR, e.PRIOR_DIAG, f"grid n={n} d={d}")
     acq_ref = o.lcb(mu_ref, np.sqrt(np.abs(var_ref)))
     assert res.best_index == int(o.first_argmax(acq_ref)[0])
     # the same sweep on an explicit copy of the grid gives bit-identical numbers
