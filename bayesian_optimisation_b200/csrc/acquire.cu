@@ -224,14 +224,6 @@ struct FinalArgs {
     const int* d_count; const long long* idx_map;   // screened sweeps: compacted survivors (count on the device, global flat index per slot)
 };
 
-__device__ __forceinline__ double acquisition_value(int kind, double mu, double sigma, double explore, double f_best) {
-    if (kind == BOGP_ACQ_LCB) return __dsub_rn(__dmul_rn(explore, sigma), mu);   // two roundings like numpy, no FMA
-    const double imp = f_best - mu;
-    if (!(sigma > 0.0)) return imp > 0.0 ? imp : 0.0;
-    const double z = imp / sigma;
-    return imp * normcdf(z) + sigma * (exp(-0.5 * z * z) * 0.3989422804014326779);
-}
-
 __device__ __forceinline__ void block_argmax(double s, long long i, double* block_score, long long* block_index, int slot) {
     __shared__ double ws[8]; __shared__ long long wi[8];
 #pragma unroll

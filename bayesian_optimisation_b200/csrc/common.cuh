@@ -199,5 +199,15 @@ __device__ __forceinline__ bool better(double s, long long i, double bs, long lo
     return (s > bs) || (s == bs && i < bi);
 }
 
+// acquisition value of one candidate: explore*sigma - mu (lower_confidence_bound, point_selector.py:204) or
+// expected improvement over f_best (minimisation)
+__device__ __forceinline__ double acquisition_value(int kind, double mu, double sigma, double explore, double f_best) {
+    if (kind == BOGP_ACQ_LCB) return __dsub_rn(__dmul_rn(explore, sigma), mu);   // two roundings like numpy, no FMA
+    const double imp = f_best - mu;
+    if (!(sigma > 0.0)) return imp > 0.0 ? imp : 0.0;
+    const double z = imp / sigma;
+    return imp * normcdf(z) + sigma * (exp(-0.5 * z * z) * 0.3989422804014326779);
+}
+
 #endif  // __CUDACC__
 }  // namespace bogp
