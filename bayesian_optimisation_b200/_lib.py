@@ -64,6 +64,8 @@ SIGNATURES = {
     "bogp_get_acquire_path": (_i32, [_vp]),
     "bogp_set_screening": (_i32, [_vp, _i32]),
     "bogp_get_screening": (_i32, [_vp]),
+    "bogp_set_fused": (_i32, [_vp, _i32, _i32]),
+    "bogp_get_fused": (_i32, [_vp]),
     "bogp_screen_stats": (_i32, [_vp, _pi64, _pi64, _i32]),
     "bogp_profile": (_i32, [_vp, _i32]),
     "bogp_profile_read": (_i32, [_vp, _i32, C.POINTER(_dbl), C.POINTER(_i64)]),

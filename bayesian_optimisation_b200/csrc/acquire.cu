@@ -418,7 +418,31 @@ using namespace bogp;
 
 extern "C" size_t bogp_acquire_workspace_bytes(const bogp_fit* fit, int64_t max_chunk) {
     if (!fit || max_chunk <= 0) return 0;
-    return acq_layout(bogp_fit_n_pad(fit), max_chunk).total;
+    const int64_t n_pad = bogp_fit_n_pad(fit);
+    const size_t chunked = acq_layout(n_pad, max_chunk).total;
+    const size_t fused = n_pad <= 16384 ? fused_workspace_bytes(n_pad) : 0;      // ring of the fused sweep kernel (INT8 path)
+    return (chunked > fused ? chunked : fused) + grid_table_reserve(n_pad);     // + the kernel-factor tables of a grid sweep
+}
+
+// The whole sweep as one launch of the fused persistent kernel (acquire_fused.cu).  Returns false if the workspace cannot
+// hold its ring (the caller then runs the separate kernels: same results); `rc` carries a launch error.
+static bool fused_sweep(bogp_ctx* ctx, const bogp_fit* fit, const CandDesc& cd, int64_t c_begin, int64_t c_end, int dim, int64_t n_pad,
+                        int kind, double explore, double f_best, double prior_diag, double* d_mu_out, double* d_sigma_out,
+                        double* d_acq_out, void* d_workspace, size_t workspace_bytes, bogp_result* d_result, cudaStream_t st,
+                        const AcqChunk& tab, int& rc) {
+    AcqChunk a{};
+    a.ft = tab.ft; a.tt = tab.tt;
+    for (int k = 0; k < BOGP_MAX_DIM; k++) { a.toff[k] = tab.toff[k]; a.lenp[k] = tab.lenp[k]; }
+    a.points = cd.points; a.axes = cd.axes; a.cross_jitter = cd.cross_jitter;
+    for (int k = 0; k < BOGP_MAX_DIM; k++) { a.len[k] = cd.len[k]; a.off[k] = cd.off[k]; }
+    a.x_pad = fit_xpad(fit); a.inv_ell2 = fit_inv_ell2(fit); a.alpha = fit_alpha(fit);
+    a.wp = fit_wp(fit); a.wq = fit_wq(fit); a.wscale = fit_wscale(fit);
+    a.c0 = c_begin; a.c_end = c_end; a.cur = c_end - c_begin; a.S = 0;
+    a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
+    FusedFinal f{d_mu_out, d_sigma_out, d_acq_out, nullptr, kind, explore, f_best, prior_diag, d_result};
+    rc = launch_acquire_fused(ctx, a, f, d_workspace, workspace_bytes, st);
+    if (rc == 1) { rc = BOGP_OK; return false; }
+    return true;
 }
 
 // All device work of one sweep, enqueued on ctx->stream without any host synchronisation.  The running winner lives in
@@ -446,6 +470,30 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         }
         if (prod != cand->c_total) { set_error("bogp_acquire: grid has %lld points, c_total says %lld", (long long)prod, (long long)cand->c_total); return BOGP_ERR_BAD_ARG; }
     }
+    // the int32 level sums of the digit-slice product are overflow-free up to K = 16384 (7 * K * 2^14 < 2^31);
+    // larger systems take the fp64 path
+    const bool use_i8 = ctx->acquire_path == BOGP_PATH_INT8_TCGEN05 && n_pad <= 16384;
+    // Grid sweeps on the INT8 path: per-axis kernel-factor tables, built once per sweep into the tail of the workspace
+    AcqChunk tab{};
+    double* gemm_f = nullptr;
+    if (use_i8 && !cd.points) {
+        tab.axes = cd.axes; tab.x_pad = fit_xpad(fit); tab.inv_ell2 = fit_inv_ell2(fit); tab.dim = dim; tab.n_pad = (int)n_pad;
+        for (int k = 0; k < BOGP_MAX_DIM; k++) { tab.len[k] = cd.len[k]; tab.off[k] = cd.off[k]; }
+        tab.n = (int)fit_n(fit);
+        const size_t tb = (grid_table_geometry(tab) + 255) / 256 * 256;
+        if (tb > 0 && tb <= grid_table_reserve(n_pad) && workspace_bytes >= tb + ((size_t)64 << 10) && workspace_bytes - tb >= acq_layout(n_pad, kAcqBN).total) {
+            workspace_bytes -= tb;
+            tab.ft = reinterpret_cast<const double*>(static_cast<char*>(d_workspace) + workspace_bytes);
+            const int trc = launch_grid_factors(ctx, tab, const_cast<double*>(tab.ft), ctx->stream);
+            if (trc) return trc;
+            // the F operand of the mean GEMM of a screened sweep (screen_gemm.cu) sits below the tables
+            const size_t fb = (gemm_screen_f_doubles(tab) * 8 + 255) / 256 * 256;
+            if (fb > 0 && tb + fb <= grid_table_reserve(n_pad) && workspace_bytes - fb >= acq_layout(n_pad, kAcqBN).total) {
+                workspace_bytes -= fb;
+                gemm_f = reinterpret_cast<double*>(static_cast<char*>(d_workspace) + workspace_bytes);
+            }
+        }
+    }
     // chunk capacity from the workspace size
     const size_t per_cand = acq_bytes_per_candidate(n_pad);
     int64_t S = (int64_t)(workspace_bytes / per_cand) / kAcqBN * kAcqBN;
@@ -464,11 +512,6 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
     cudaStream_t st = ctx->stream;
     double* best = &d_result->score; long long* besti = reinterpret_cast<long long*>(&d_result->index);
     int* nan_flag = &d_result->nan_flag;
-    init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
-
-    // the int32 level sums of the digit-slice product are overflow-free up to K = 16384 (7 * K * 2^14 < 2^31);
-    // larger systems take the fp64 path
-    const bool use_i8 = ctx->acquire_path == BOGP_PATH_INT8_TCGEN05 && n_pad <= 16384;
     {   // the fit packs W for the path selected at fit time; a later switch packs on first use
         const int prc = fit_ensure_packed(ctx, fit, use_i8 ? BOGP_PATH_INT8_TCGEN05 : BOGP_PATH_FP64_DMMA);
         if (prc) return prc;
@@ -485,9 +528,23 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         BOGP_PROFILED(ctx, BOGP_PROF_MERGE, (merge_kernel<<<1, 256, 0, st>>>(ctx->d_block_score, ctx->d_block_index, nfb, best, besti))); BOGP_LAUNCH_CHECK(ctx);
         return BOGP_OK;
     };
+    int fused_rc = BOGP_OK;
     const bool want_out = d_mu_out || d_sigma_out || d_acq_out;
     const bool screen = use_i8 && ctx->screening && !want_out && !ctx->profile && cand->cross_jitter == 0.0 && prior_diag >= 1.0 &&
                         (kind == BOGP_ACQ_EI || explore >= 0.0) && (c_end - c_begin) >= 4 * kScreenSeed && S >= kScreenSeed;
+    bool fused_done = false;
+    if (!screen && use_i8 && ctx->fused) {
+        fused_done = fused_sweep(ctx, fit, cd, c_begin, c_end, dim, n_pad, kind, explore, f_best, prior_diag,
+                                 d_mu_out, d_sigma_out, d_acq_out, d_workspace, workspace_bytes, d_result, st, tab, fused_rc);
+        if (fused_rc) return fused_rc;
+    }
+    if (fused_done) return BOGP_OK;
+    if (screen && gemm_f) {
+        // grid sweep: the means of all candidates from GEMMs, survivors scored exactly (screen_gemm.cu)
+        const int grc = gemm_screen_sweep(ctx, fit, tab, c_begin, c_end, kind, explore, f_best, prior_diag, d_workspace, workspace_bytes, gemm_f, d_result);
+        if (grc != 1) return grc;
+    }
+    init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);
     if (screen) {
         // One buffer set of S candidates.  The tail of the panel region (the digits take 7 of its 8 bytes per entry)
         // holds the compacted survivors: coordinates, global flat indices and the device-side count.
@@ -499,7 +556,11 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         const int64_t total = c_end - c_begin;
         auto make_chunk = [&](int64_t c0, int64_t cur_cap, bool compacted) {
             AcqChunk a{};
-            a.points = compacted ? surv_pts : cd.points; a.axes = compacted ? nullptr : cd.axes; a.cross_jitter = 0.0;
+            // compacted survivors of a grid sweep with tables: scored from their flat indices through the same tables (same bits
+            // as inside the contiguous sweep); otherwise from their gathered coordinates
+            const bool by_index = compacted && tab.ft != nullptr;
+            a.points = (compacted && !by_index) ? surv_pts : cd.points; a.axes = (compacted && !by_index) ? nullptr : cd.axes; a.cross_jitter = 0.0;
+            a.idx_list = by_index ? surv_idx : nullptr;
             for (int k = 0; k < BOGP_MAX_DIM; k++) { a.len[k] = cd.len[k]; a.off[k] = cd.off[k]; }
             a.x_pad = fit_xpad(fit); a.inv_ell2 = fit_inv_ell2(fit); a.alpha = fit_alpha(fit);
             a.wp = fit_wp(fit); a.wq = fit_wq(fit); a.wscale = fit_wscale(fit);
@@ -507,6 +568,7 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
             a.c0 = compacted ? 0 : c0; a.c_end = compacted ? cur_cap : c_end; a.cur = cur_cap; a.S = S;
             a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
             a.d_count = compacted ? count : nullptr;
+            if (!compacted || by_index) { a.ft = tab.ft; a.tt = tab.tt; for (int k = 0; k < BOGP_MAX_DIM; k++) { a.toff[k] = tab.toff[k]; a.lenp[k] = tab.lenp[k]; } }
             return a;
         };
         auto exact_pass = [&](int64_t cap) -> int {          // the survivors in surv_pts[0 .. *count), at most `cap`
@@ -536,7 +598,7 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
             rc = exact_pass((cur + kAcqBN - 1) / kAcqBN * kAcqBN); if (rc) return rc;
         }
     } else if (use_i8) {
-        // INT8 path.  The panel kernel (FP64/INT pipes) and the tensor-core kernel use different
+        // INT8 path, separate kernels.  The panel kernel (FP64/INT pipes) and the tensor-core kernel use different
         // pipes and fit on one SM together, so with two buffer sets the panel of chunk s+1 is built
         // on a second stream while chunk s is on the tensor cores.
         const int64_t total = c_end - c_begin;
@@ -555,6 +617,7 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
             a.panel = bb + lb.panel; a.qpart = (double*)(bb + lb.qpart); a.mupart = (double*)(bb + lb.mupart);
             a.c0 = c0; a.c_end = c_end; a.cur = (c_end - c0 < Sb) ? (c_end - c0) : Sb; a.S = Sb;
             a.n = (int)fit_n(fit); a.n_pad = (int)n_pad; a.dim = dim;
+            a.ft = tab.ft; a.tt = tab.tt; for (int k = 0; k < BOGP_MAX_DIM; k++) { a.toff[k] = tab.toff[k]; a.lenp[k] = tab.lenp[k]; }
             return a;
         };
         cudaStream_t ps = overlap ? ctx->aux_stream : st;

@@ -72,10 +72,69 @@ __global__ void __launch_bounds__(256) slice_w_kernel(const double* __restrict__
         *reinterpret_cast<uint4*>(dst + p * (kI8BM * kI8KB)) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
 }
 
+// Per-axis kernel-factor tables of a grid sweep: ft[toff[k] + j * lenp[k] + g] = exp(-0.5 (axis_k[g] - x_jk)^2 / ell_k^2),
+// the operations of one term of every other kernel-function site.  grid (ceil(n_pad * lenp_k / 256), dim).
+__global__ void __launch_bounds__(256) grid_factor_kernel(GridTabArgs a) {
+    const int k = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)a.n_pad * a.lenp[k]) return;
+    const int64_t j = i / a.lenp[k];
+    const int g = (int)(i - j * a.lenp[k]);
+    double v = 0.0;
+    if (g < a.len[k]) {
+        const double d = a.axes[a.off[k] + g] - a.x_pad[j * a.dim + k];
+        v = exp_nonpos(-0.5 * ((d * d) * a.inv_ell2[k]));
+    }
+    a.ft[a.toff[k] + i] = v;
+    if (g < a.len[k]) a.ft[a.toffT[k] + (int64_t)g * a.n_pad + j] = v;      // transposed copy: rows over j
+}
+
+size_t grid_table_reserve(int64_t n_pad) {
+    const size_t full = (size_t)n_pad * BOGP_MAX_DIM * 64 * 8;      // tables (both layouts) ...
+    return (full < ((size_t)64 << 20) ? full : ((size_t)64 << 20)) + (size_t)n_pad * 256 * 8 + 4096;   // ... + the F operand of the mean GEMM
+}
+
+size_t grid_table_geometry(AcqChunk& a) {
+    a.ft = nullptr;
+    if (a.points || !a.axes) return 0;
+    // trailing axes multiplied per entry: the fewest whose grid points number at least one tile (64), so that a tile sees
+    // at most two settings of the leading axes; their table rows are staged in shared memory, 16 grid points per row
+    int tt = 0; int64_t prod = 1;
+    while (tt < a.dim && prod < kI8BN) { tt++; prod *= a.len[a.dim - tt]; }
+    if (tt < 1 || tt > 3) return 0;
+    for (int t = 0; t < tt; t++) if (a.len[a.dim - 1 - t] > 16) return 0;
+    a.tt = tt;
+    int64_t off = 0;
+    for (int k = 0; k < a.dim; k++) {
+        a.lenp[k] = (a.len[k] + 15) / 16 * 16;          // rows of whole 128-byte lines (the trailing axes: exactly one)
+        if (off > (int64_t)0x7fffffff) return 0;
+        a.toff[k] = (int)off;
+        off += (int64_t)a.n_pad * a.lenp[k];
+    }
+    for (int k = 0; k < a.dim; k++) {                   // transposed copies
+        if (off > (int64_t)0x7fffffff) return 0;
+        a.toffT[k] = (int)off;
+        off += (int64_t)a.n_pad * a.len[k];
+    }
+    return (size_t)off * 8;
+}
+
+int launch_grid_factors(bogp_ctx* ctx, const AcqChunk& a, double* d_ft, cudaStream_t stream) {
+    GridTabArgs g{};
+    g.axes = a.axes; g.x_pad = a.x_pad; g.inv_ell2 = a.inv_ell2; g.ft = d_ft; g.dim = a.dim; g.n_pad = a.n_pad;
+    int maxlen = 0;
+    for (int k = 0; k < BOGP_MAX_DIM; k++) { g.len[k] = a.len[k]; g.off[k] = a.off[k]; g.toff[k] = a.toff[k]; g.lenp[k] = a.lenp[k]; g.toffT[k] = a.toffT[k]; if (k < a.dim && a.lenp[k] > maxlen) maxlen = a.lenp[k]; }
+    const dim3 grid((unsigned)(((int64_t)a.n_pad * maxlen + 255) / 256), a.dim);
+    grid_factor_kernel<<<grid, 256, 0, stream>>>(g);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
+}
+
 // stand-alone panel kernel: grid (ceil(cur/64), n_pad/256), 256 threads, one panel tile per CTA
 template <int DIMP, bool UB, bool MUONLY>
 __global__ void __launch_bounds__(256, 3) panel_i8_kernel(PanelI8Args p) {
-    __shared__ PanelSmem<DIMP> sm;
+    extern __shared__ __align__(128) unsigned char panel_smem_raw[];
+    PanelSmem<DIMP>& sm = *reinterpret_cast<PanelSmem<DIMP>*>(panel_smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -249,18 +308,24 @@ size_t i8_panel_bytes(int64_t n_pad, int64_t S) { return (size_t)n_pad * S * kI8
 int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream, bool mu_only) {
     const int nct = (int)((a.cur + kI8BN - 1) / kI8BN);
     PanelI8Args pa{};
-    pa.d_count = a.d_count;
-    pa.cand.points = a.points; pa.cand.axes = a.axes; pa.cand.cross_jitter = a.cross_jitter;
-    for (int k = 0; k < BOGP_MAX_DIM; k++) { pa.cand.len[k] = a.len[k]; pa.cand.off[k] = a.off[k]; }
+    pa.d_count = a.d_count; pa.idx_list = a.idx_list;
+    fill_cand(pa.cand, a);
     pa.x_pad = a.x_pad; pa.inv_ell2 = a.inv_ell2; pa.alpha = a.alpha; pa.panel = (uint8_t*)a.panel; pa.mupart = a.mupart;
     pa.c0 = a.c0; pa.c_end = a.c_end; pa.S = a.S; pa.n = a.n; pa.n_pad = a.n_pad; pa.dim = a.dim;
     const bool ub = a.n_pad <= 8192;      // unsigned panel digits while the int32 level sums cannot overflow
     const dim3 pgrid(nct, a.n_pad / kAcqBM);
 #define BOGP_PANEL_I8(D)                                                                                                 \
     do {                                                                                                                 \
-        if (mu_only) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true, true><<<pgrid, 256, 0, stream>>>(pa))); }  \
-        else if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true, false><<<pgrid, 256, 0, stream>>>(pa))); } \
-        else         { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false, false><<<pgrid, 256, 0, stream>>>(pa))); }\
+        static DeviceOnce once;                                                                                          \
+        const size_t psm = sizeof(PanelSmem<D>);                                                                         \
+        if (once.need(ctx->device)) {                                                                                    \
+            BOGP_CUDA_CHECK(cudaFuncSetAttribute(panel_i8_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));   \
+            BOGP_CUDA_CHECK(cudaFuncSetAttribute(panel_i8_kernel<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));  \
+            BOGP_CUDA_CHECK(cudaFuncSetAttribute(panel_i8_kernel<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); \
+        }                                                                                                                \
+        if (mu_only) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true, true><<<pgrid, 256, psm, stream>>>(pa))); }  \
+        else if (ub) { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, true, false><<<pgrid, 256, psm, stream>>>(pa))); } \
+        else         { BOGP_PROFILED(ctx, BOGP_PROF_PANEL, (panel_i8_kernel<D, false, false><<<pgrid, 256, psm, stream>>>(pa))); }\
     } while (0)
     if (a.dim <= 2) BOGP_PANEL_I8(2); else if (a.dim <= 4) BOGP_PANEL_I8(4); else if (a.dim <= 6) BOGP_PANEL_I8(6);
     else if (a.dim <= 8) BOGP_PANEL_I8(8); else if (a.dim <= 10) BOGP_PANEL_I8(10); else if (a.dim <= 12) BOGP_PANEL_I8(12);

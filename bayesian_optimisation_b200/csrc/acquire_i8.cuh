@@ -38,6 +38,14 @@ struct CandDescI8 {
     const double* points; const double* axes;
     int len[BOGP_MAX_DIM]; int off[BOGP_MAX_DIM];
     double cross_jitter;
+    // Grid sweeps: per-axis kernel-factor tables, ft[toff[k] + j * lenp[k] + g] =
+    // exp(-0.5 (axis_k[g] - x_jk)^2 / ell_k^2), built once per sweep by grid_factor_kernel.  A grid entry is then the
+    // product k_*[j, c] = (((1 f_0) f_1) ... f_{d-1}) of d table values, always in this order, so its bits do not depend on
+    // the tile, chunk or GPU that computes it.  The product over the leading d - tt axes is formed once per row and
+    // setting of those axes (a 64-candidate tile sees at most two), the trailing tt factors come from table rows staged
+    // in shared memory.  Null: every entry is exp(-0.5 * squared distance) (explicit candidate arrays, long axes).
+    const double* ft; int toff[BOGP_MAX_DIM]; int lenp[BOGP_MAX_DIM];
+    int tt;     // trailing axes multiplied per entry (the smallest count whose grid points number >= 64: a tile then sees at most two settings of the leading axes)
 };
 struct PanelI8Args {
     CandDescI8 cand;
@@ -46,6 +54,7 @@ struct PanelI8Args {
     int64_t c0, c_end, S;
     int n, n_pad, dim;
     const int* d_count;       // screened sweeps: number of valid candidates of the (compacted) array lives on the device
+    const long long* idx_list; // screened grid sweeps: slot -> flat grid index of the compacted survivors (table mode, scattered candidates)
 };
 
 // 4x4 byte transpose: out[m] = (byte m of w0, byte m of w1, byte m of w2, byte m of w3)
@@ -86,33 +95,47 @@ __device__ __forceinline__ double kstar_row(double s, const double (&pc)[DIMP], 
     return exp_nonpos(-0.5 * s, etab);
 }
 
+// Value sources of panel_rows: k_*(x_jl, candidate of this thread) for row jl of the 256-row block.
+template <int DIMP, int T>
+struct ExpSrc {                      // exp of the squared distance; prefix sums of the shared leading dimensions in `pre`
+    const double (&pc)[DIMP]; const double (&il)[DIMP]; const double* xs; const double* etab; const double* pre;
+    __device__ __forceinline__ double eval(int jl) const { return kstar_row<DIMP, T>(T < DIMP ? pre[jl] : 0.0, pc, il, xs + jl * DIMP, etab); }
+};
+template <int TT>
+struct TabSrc {                      // prefix product of the leading axes (per row) x TT staged table rows at this candidate's grid points
+    const double* pre; const double* st; int dig[TT]; int row0;      // st: [t][64 rows][16]; row0 = first row of the staged piece
+    __device__ __forceinline__ double eval(int jl) const {
+        double v = pre[jl];
+#pragma unroll
+        for (int t = 0; t < TT; t++) v *= st[(t * 64 + (jl - row0)) * 16 + dig[t]];
+        return v;
+    }
+};
+
 // the row groups of one panel tile for one thread (= one candidate): digits + partial posterior mean
 struct PanelRowCtx {
-    const double* xs; const double* al; const double* etab; const double* pre;     // shared memory
+    const double* al;                 // shared memory
     uint8_t* panel; int64_t tile_base;    // (ct * (n_pad / 32) + jb * 8) * kI8BTile
     int nvr, jq, nl, tid; double jit;
 };
 
 // MUONLY: the screening pass of an arg-max-only sweep -- the same k_* values and the same partial posterior means
 // (same operations, same order: bit-identical mu), but no digits are formed or stored.
-template <int DIMP, bool UB, int T, bool MUONLY>
-__device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double (&pc)[DIMP], const double (&il)[DIMP]) {
-    double mu = 0.0;      // this thread's 4 row groups, ascending
-    // 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12
-    for (int g = c.tid >> 6; g < kAcqBM / 16; g += 4) {
+template <bool UB, bool MUONLY, class SRC>
+__device__ __forceinline__ double panel_group(const PanelRowCtx& c, const SRC& src, int g) {
+    {
         uint32_t pk[kI8Slices][4];
         double mug = 0.0;
         if (MUONLY) {
 #pragma unroll 4
             for (int e = 0; e < 16; e++) {
                 const int jl = g * 16 + e;
-                double v = kstar_row<DIMP, T>(T < DIMP ? c.pre[jl] : 0.0, pc, il, c.xs + jl * DIMP, c.etab);
+                double v = src.eval(jl);
                 v = jl < c.nvr ? v : 0.0;
                 if (jl == c.jq) v += c.jit;
                 mug += c.al[jl] * v;
             }
-            mu += mug;
-            continue;
+            return mug;
         }
         if (UB) {
 #pragma unroll
@@ -121,7 +144,7 @@ __device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double 
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int jl = g * 16 + e4 * 4 + i;
-                    double v = kstar_row<DIMP, T>(T < DIMP ? c.pre[jl] : 0.0, pc, il, c.xs + jl * DIMP, c.etab);
+                    double v = src.eval(jl);
                     v = jl < c.nvr ? v : 0.0;
                     if (jl == c.jq) v += c.jit;
                     mug += c.al[jl] * v;
@@ -140,7 +163,7 @@ __device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double 
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 const int jl = g * 16 + e;
-                double v = kstar_row<DIMP, T>(T < DIMP ? c.pre[jl] : 0.0, pc, il, c.xs + jl * DIMP, c.etab);
+                double v = src.eval(jl);
                 v = jl < c.nvr ? v : 0.0;
                 if (jl == c.jq) v += c.jit;
                 mug += c.al[jl] * v;
@@ -150,25 +173,35 @@ __device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const double 
                 for (int m = 0; m < kI8Slices; m++) pk[kI8Slices - 1 - m][e >> 2] |= (uint32_t)(d[m] & 0xFF) << (8 * (e & 3));
             }
         }
-        mu += mug;
         // k tile (32 rows) = jb*8 + g/2, k chunk = g & 1
         uint8_t* dst = c.panel + (c.tile_base + (g >> 1)) * kI8BTile + (g & 1) * (kI8Slices * kI8BN * 16) + c.nl * 16;
 #pragma unroll
         for (int q = 0; q < kI8Slices; q++)
             *reinterpret_cast<uint4*>(dst + q * (kI8BN * 16)) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+        return mug;
     }
+}
+
+// 16 groups of 16 rows; this thread takes groups g = tid/64, +4, +8, +12, ascending
+template <bool UB, bool MUONLY, class SRC>
+__device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const SRC& src) {
+    double mu = 0.0;
+    for (int g = c.tid >> 6; g < kAcqBM / 16; g += 4) mu += panel_group<UB, MUONLY>(c, src, g);
     return mu;
 }
 
 template <int DIMP>
 struct PanelSmem {
     alignas(128) double ps_raw[kI8BN * BOGP_MAX_DIM];   // candidate block, [cand][dim] as in HBM
-    alignas(16) double xs[kAcqBM][DIMP];
+    union {
+        alignas(16) double xs[kAcqBM][DIMP];                // exp mode: the 256 measured points of the row block
+        alignas(16) double stage[3 * 64 * 16];              // table mode: 64 rows of up to three trailing axes' tables
+    };
     double al[kAcqBM];
     double sl[BOGP_MAX_DIM];
     double etab[64];
     double mured[4][kI8BN];
-    double pre[kAcqBM];
+    double pre[2][kAcqBM];                                  // exp mode: [0] prefix sums; table mode: prefix products of the two leading-axis settings
     int kshare;
     alignas(8) uint64_t bar;                            // bulk-TMA staging of explicit candidate blocks (caller initialises, count 1)
 };
@@ -178,6 +211,122 @@ struct PanelSmem {
 template <bool NAMED>
 __device__ __forceinline__ void panel_sync() {
     if (NAMED) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads();
+}
+
+// Table mode of panel_tile (grid sweeps): called after the grid digits of the tile's candidates are in shared memory.
+// Rows go in four pieces of 64; the table rows of the trailing axes of a piece (64 rows x 16 grid points x tt axes, one
+// contiguous 8 KB block per axis) are staged in shared memory -- the next piece travels to registers while the current one
+// is worked on -- so an entry costs tt shared-memory loads and multiplications instead of a squared distance and an exp.
+template <int DIMP, bool UB, bool MUONLY, bool NAMED, int TT>
+__device__ __forceinline__ double panel_tile_table_rows(const PanelI8Args& p, const PanelRowCtx& rc, int jb, PanelSmem<DIMP>& sm, int tid,
+                                                        const double* pre, const int* mydig) {
+    const int kl = p.dim - TT;
+    TabSrc<TT> src; src.pre = pre; src.st = sm.stage;
+#pragma unroll
+    for (int t = 0; t < TT; t++) src.dig[t] = mydig[kl + t];
+    // piece r of axis t: 64 rows x 16 doubles = 512 x 16 B; thread tid moves vectors tid and tid + 256
+    uint4 nx[TT][2];
+    auto fetch = [&](int r) {
+#pragma unroll
+        for (int t = 0; t < TT; t++) {
+            const uint4* src4 = reinterpret_cast<const uint4*>(p.cand.ft + p.cand.toff[kl + t] + ((int64_t)jb * kAcqBM + r * 64) * 16);
+            nx[t][0] = __ldg(src4 + tid); nx[t][1] = __ldg(src4 + tid + 256);
+        }
+    };
+    fetch(0);
+    double mu = 0.0;
+    for (int r = 0; r < 4; r++) {
+        uint4* st4 = reinterpret_cast<uint4*>(sm.stage);
+#pragma unroll
+        for (int t = 0; t < TT; t++) { st4[t * 512 + tid] = nx[t][0]; st4[t * 512 + tid + 256] = nx[t][1]; }
+        panel_sync<NAMED>();
+        if (r < 3) fetch(r + 1);
+        src.row0 = r * 64;
+        mu += panel_group<UB, MUONLY>(rc, src, 4 * r + (tid >> 6));
+        panel_sync<NAMED>();                       // everybody is done with the staged piece
+    }
+    return mu;
+}
+
+template <int DIMP, bool UB, bool MUONLY, bool NAMED>
+__device__ __forceinline__ bool panel_tile_table(const PanelI8Args& p, int64_t cbase, int64_t ct_store, int jb, int nvalid,
+                                                 PanelSmem<DIMP>& sm, int tid) {
+    const int dim = p.dim, tt = p.cand.tt, kl = dim - tt;
+    const int* dg = reinterpret_cast<const int*>(sm.ps_raw);
+    const int last = nvalid - 1;
+    {   // prefix products over the leading axes, (((1 f_0) f_1) ... f_{kl-1}), for the settings of the first and the last candidate
+        const int64_t j = (int64_t)jb * kAcqBM + tid;
+        double v0 = 1.0, v1 = 1.0;
+        for (int k = 0; k < kl; k++) {
+            const double* row = p.cand.ft + p.cand.toff[k] + j * p.cand.lenp[k];
+            v0 *= __ldg(row + dg[k]); v1 *= __ldg(row + dg[last * BOGP_MAX_DIM + k]);
+        }
+        sm.pre[0][tid] = v0; sm.pre[1][tid] = v1;
+    }
+    const int nl = tid & 63;
+    const int ncl = nl < nvalid ? nl : last;
+    const int* mydig = dg + ncl * BOGP_MAX_DIM;
+    bool second = false;                           // this candidate sits on the last candidate's setting of the leading axes
+    for (int k = 0; k < kl; k++) second |= mydig[k] != dg[k];
+    PanelRowCtx rc;
+    rc.al = sm.al;
+    rc.panel = p.panel; rc.tile_base = ct_store * (p.n_pad / kI8KB) + (int64_t)jb * (kAcqBM / kI8KB);
+    rc.nvr = p.n - jb * kAcqBM;
+    const int64_t jq64 = (cbase + nl) - (int64_t)jb * kAcqBM;
+    rc.jq = (p.cand.cross_jitter != 0.0 && jq64 >= 0 && jq64 < kAcqBM) ? (int)jq64 : -1;
+    rc.jit = p.cand.cross_jitter; rc.nl = nl; rc.tid = tid;
+    const double* pre = sm.pre[second ? 1 : 0];
+    double mu;
+    if (tt == 1)      mu = panel_tile_table_rows<DIMP, UB, MUONLY, NAMED, 1>(p, rc, jb, sm, tid, pre, mydig);
+    else if (tt == 2) mu = panel_tile_table_rows<DIMP, UB, MUONLY, NAMED, 2>(p, rc, jb, sm, tid, pre, mydig);
+    else              mu = panel_tile_table_rows<DIMP, UB, MUONLY, NAMED, 3>(p, rc, jb, sm, tid, pre, mydig);
+    sm.mured[tid >> 6][nl] = mu;
+    panel_sync<NAMED>();
+    if (tid < kI8BN) {                              // fixed-order sum of the 4 thread groups
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) s += sm.mured[g][tid];
+        p.mupart[(int64_t)jb * p.S + ct_store * kI8BN + tid] = s;
+    }
+    return true;
+}
+
+// Table mode for candidates scattered over the grid (the compacted survivors of a screened sweep): the same ordered product
+// (((1 f_0) f_1) ... f_{d-1}) with every factor read from the tables in L2 -- the same bits as panel_tile_table gives the
+// candidate inside a contiguous sweep, at the price of d dependent-latency loads per entry (survivors are few).
+struct TabSrcAll {
+    const double* tp[BOGP_MAX_DIM]; int stride[BOGP_MAX_DIM]; int dim;
+    __device__ __forceinline__ double eval(int jl) const {
+        double v = 1.0;
+        for (int k = 0; k < dim; k++) v *= __ldg(tp[k] + (int64_t)jl * stride[k]);
+        return v;
+    }
+};
+template <int DIMP, bool UB, bool MUONLY, bool NAMED>
+__device__ __forceinline__ bool panel_tile_scattered(const PanelI8Args& p, int64_t cbase, int64_t ct_store, int jb, int nvalid,
+                                                     PanelSmem<DIMP>& sm, int tid) {
+    const int* dg = reinterpret_cast<const int*>(sm.ps_raw);
+    const int nl = tid & 63;
+    const int ncl = nl < nvalid ? nl : nvalid - 1;
+    TabSrcAll src; src.dim = p.dim;
+    for (int k = 0; k < p.dim; k++) {
+        src.stride[k] = p.cand.lenp[k];
+        src.tp[k] = p.cand.ft + p.cand.toff[k] + (int64_t)jb * kAcqBM * p.cand.lenp[k] + dg[ncl * BOGP_MAX_DIM + k];
+    }
+    PanelRowCtx rc;
+    rc.al = sm.al;
+    rc.panel = p.panel; rc.tile_base = ct_store * (p.n_pad / kI8KB) + (int64_t)jb * (kAcqBM / kI8KB);
+    rc.nvr = p.n - jb * kAcqBM;
+    rc.jq = -1; rc.jit = 0.0; rc.nl = nl; rc.tid = tid;
+    sm.mured[tid >> 6][nl] = panel_rows<UB, MUONLY>(rc, src);
+    panel_sync<NAMED>();
+    if (tid < kI8BN) {                              // fixed-order sum of the 4 thread groups
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) s += sm.mured[g][tid];
+        p.mupart[(int64_t)jb * p.S + ct_store * kI8BN + tid] = s;
+    }
+    return true;
 }
 
 // One panel tile: candidates [c0 + 64 ct, +64) x rows [256 jb, +256): digits into tile slot `ct_store` of p.panel,
@@ -204,9 +353,12 @@ __device__ __forceinline__ bool panel_tile(const PanelI8Args& p, int64_t ct, int
             if (tid == 0) { mbar_expect_tx(&sm.bar, bytes); bulk_g2s(sm.ps_raw, src, bytes, &sm.bar); }
         }
     }
-    for (int i = tid; i < kAcqBM * DIMP; i += 256) {
-        int r = i / DIMP, k = i % DIMP;
-        sm.xs[r][k] = k < dim ? p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k] : 0.0;
+    const bool table = !explicit_mode && p.cand.ft != nullptr;
+    if (!table) {
+        for (int i = tid; i < kAcqBM * DIMP; i += 256) {
+            int r = i / DIMP, k = i % DIMP;
+            sm.xs[r][k] = k < dim ? p.x_pad[((int64_t)jb * kAcqBM + r) * dim + k] : 0.0;
+        }
     }
     sm.al[tid] = p.alpha[jb * kAcqBM + tid];
     if (tid < BOGP_MAX_DIM) sm.sl[tid] = tid < dim ? p.inv_ell2[tid] : 0.0;
@@ -215,15 +367,19 @@ __device__ __forceinline__ bool panel_tile(const PanelI8Args& p, int64_t ct, int
         if (used_tma) { mbar_wait(&sm.bar, tma_phase); tma_phase ^= 1u; }
         else for (int i = tid; i < nvalid * dim; i += 256) sm.ps_raw[i] = p.cand.points[cbase * dim + i];
     } else if (tid < nvalid) {
-        int64_t f = cbase + tid;
+        int64_t f = p.idx_list ? p.idx_list[cbase + tid] : cbase + tid;
+        int* dg = reinterpret_cast<int*>(sm.ps_raw) + tid * BOGP_MAX_DIM;     // table mode: grid digits instead of coordinates
         for (int k = dim - 1; k >= 0; k--) {
             const int64_t q = f / p.cand.len[k];
-            sm.ps_raw[tid * dim + k] = p.cand.axes[p.cand.off[k] + (int)(f - q * p.cand.len[k])];
+            const int g = (int)(f - q * p.cand.len[k]);
+            if (table) dg[k] = g; else sm.ps_raw[tid * dim + k] = p.cand.axes[p.cand.off[k] + g];
             f = q;
         }
     }
     if (tid == 0) sm.kshare = DIMP;
     panel_sync<NAMED>();
+    if (table && p.idx_list) return panel_tile_scattered<DIMP, UB, MUONLY, NAMED>(p, cbase, ct_store, jb, nvalid, sm, tid);
+    if (table) return panel_tile_table<DIMP, UB, MUONLY, NAMED>(p, cbase, ct_store, jb, nvalid, sm, tid);
 
     // Leading coordinates that ALL candidates of the tile share (a grid sweep: all but the last two or three axes):
     // their part of the squared distance is computed once per row instead of once per entry.  Detected at run time on
@@ -243,7 +399,7 @@ __device__ __forceinline__ bool panel_tile(const PanelI8Args& p, int64_t ct, int
             const double d0 = (k < dim ? sm.ps_raw[k] : 0.0) - sm.xs[tid][k];
             s0 += (d0 * d0) * sm.sl[k];
         }
-        sm.pre[tid] = s0;
+        sm.pre[0][tid] = s0;
     }
     panel_sync<NAMED>();
 
@@ -253,7 +409,7 @@ __device__ __forceinline__ bool panel_tile(const PanelI8Args& p, int64_t ct, int
 #pragma unroll
     for (int k = 0; k < DIMP; k++) { pc[k] = k < dim ? sm.ps_raw[ncl * dim + k] : 0.0; il[k] = sm.sl[k]; }
     PanelRowCtx rc;
-    rc.xs = &sm.xs[0][0]; rc.al = sm.al; rc.etab = sm.etab; rc.pre = sm.pre;
+    rc.al = sm.al;
     rc.panel = p.panel; rc.tile_base = ct_store * (p.n_pad / kI8KB) + (int64_t)jb * (kAcqBM / kI8KB);
     rc.nvr = p.n - jb * kAcqBM;                    // rows of this block that are real measurements (the rest is padding: k_* = 0)
     // row of this block on which the reference's shape-equality jitter falls for this candidate (-1: none)
@@ -261,10 +417,11 @@ __device__ __forceinline__ bool panel_tile(const PanelI8Args& p, int64_t ct, int
     rc.jq = (p.cand.cross_jitter != 0.0 && jq64 >= 0 && jq64 < kAcqBM) ? (int)jq64 : -1;
     rc.jit = p.cand.cross_jitter; rc.nl = nl; rc.tid = tid;
     double mu;
-    if (DIMP > 4 && T == 2)      mu = panel_rows<DIMP, UB, (DIMP > 4 ? 2 : DIMP), MUONLY>(rc, pc, il);
-    else if (DIMP > 4 && T == 3) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 3 : DIMP), MUONLY>(rc, pc, il);
-    else if (DIMP > 4 && T == 4) mu = panel_rows<DIMP, UB, (DIMP > 4 ? 4 : DIMP), MUONLY>(rc, pc, il);
-    else                         mu = panel_rows<DIMP, UB, DIMP, MUONLY>(rc, pc, il);
+    const double* xs0 = &sm.xs[0][0];
+    if (DIMP > 4 && T == 2)      mu = panel_rows<UB, MUONLY>(rc, ExpSrc<DIMP, (DIMP > 4 ? 2 : DIMP)>{pc, il, xs0, sm.etab, sm.pre[0]});
+    else if (DIMP > 4 && T == 3) mu = panel_rows<UB, MUONLY>(rc, ExpSrc<DIMP, (DIMP > 4 ? 3 : DIMP)>{pc, il, xs0, sm.etab, sm.pre[0]});
+    else if (DIMP > 4 && T == 4) mu = panel_rows<UB, MUONLY>(rc, ExpSrc<DIMP, (DIMP > 4 ? 4 : DIMP)>{pc, il, xs0, sm.etab, sm.pre[0]});
+    else                         mu = panel_rows<UB, MUONLY>(rc, ExpSrc<DIMP, DIMP>{pc, il, xs0, sm.etab, sm.pre[0]});
     sm.mured[tid >> 6][nl] = mu;
     panel_sync<NAMED>();
     if (tid < kI8BN) {                              // fixed-order sum of the 4 thread groups
@@ -314,6 +471,18 @@ struct TriI8Args {
 // low mantissa bits, and subtracting the constant is exact.
 __device__ __forceinline__ double i32_bits_to_f64(uint32_t r) {
     return __hiloint2double(0x43300000, (int)(r ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// per-axis kernel-factor tables of a grid sweep; one thread per (axis, row, padded grid point)
+struct GridTabArgs {
+    const double* axes; const double* x_pad; const double* inv_ell2; double* ft;
+    int len[BOGP_MAX_DIM]; int off[BOGP_MAX_DIM]; int toff[BOGP_MAX_DIM]; int lenp[BOGP_MAX_DIM]; int toffT[BOGP_MAX_DIM];
+    int dim, n_pad;
+};
+// PanelI8Args.cand from a chunk descriptor
+__host__ inline void fill_cand(CandDescI8& c, const AcqChunk& a) {
+    c.points = a.points; c.axes = a.axes; c.cross_jitter = a.cross_jitter; c.ft = a.points ? nullptr : a.ft; c.tt = a.tt;
+    for (int k = 0; k < BOGP_MAX_DIM; k++) { c.len[k] = a.len[k]; c.off[k] = a.off[k]; c.toff[k] = a.toff[k]; c.lenp[k] = a.lenp[k]; }
 }
 
 constexpr int kI8Threads = 320;      // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue

@@ -85,6 +85,8 @@ struct bogp_ctx {
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
     int          screening;     // arg-max-only sweeps: screen by the posterior-mean bound, score survivors exactly (bogp_set_screening)
+    int          fused;         // INT8 path: one persistent fused kernel per sweep (default) instead of per-chunk panel / product / finalize / merge kernels
+    int          fused_group;   // candidate tiles per work group of the fused kernel (0 = automatic: ~32 MB of panel digits)
     cudaEvent_t  ev[2];
     double       prof_ms[8];
     int64_t      prof_n[8];

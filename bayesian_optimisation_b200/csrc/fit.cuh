@@ -35,9 +35,32 @@ struct AcqChunk {
     int64_t c0, c_end, cur, S;
     int n, n_pad, dim;
     const int* d_count;               // screened sweeps: the candidates are a compacted array whose length lives on the device
+    const long long* idx_list;        // screened grid sweeps: slot -> flat grid index of the compacted survivors
+    const double* ft; int toff[BOGP_MAX_DIM]; int lenp[BOGP_MAX_DIM]; int tt;   // grid sweeps: per-axis kernel-factor tables (acquire_i8.cuh), or null
+    int toffT[BOGP_MAX_DIM];          // the same tables transposed, ft[toffT[k] + g * n_pad + j] (rows over j: operands of the mean GEMM, screen_gemm.cu)
 };
 int launch_panel_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream, bool mu_only = false);
 int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream);
+// the fused persistent sweep kernel (acquire_fused.cu): finalisation parameters and outputs of one sweep
+struct FusedFinal {
+    double* mu_out; double* sigma_out; double* acq_out;      // indexed by candidate - c0 (or null)
+    const long long* idx_map;                                // compacted sweeps: global flat index per slot
+    int kind; double explore, f_best, prior;
+    bogp_result* result;                                     // device record the winner is written to
+    int fold_prev;                                           // 1: the record already holds a running winner, fold it in
+};
+int launch_acquire_fused(bogp_ctx* ctx, const AcqChunk& a, const FusedFinal& f, void* d_workspace, size_t workspace_bytes, cudaStream_t st);
+size_t fused_workspace_bytes(int64_t n_pad);
+// per-axis kernel-factor tables of a grid sweep: geometry (returns the size in bytes, 0 if `a` is not a grid) and build
+size_t grid_table_geometry(AcqChunk& a);
+int launch_grid_factors(bogp_ctx* ctx, const AcqChunk& a, double* d_ft, cudaStream_t stream);
+size_t grid_table_reserve(int64_t n_pad);
+// Screened arg-max-only grid sweep with the posterior means of ALL candidates from one fp64 GEMM per chunk (screen_gemm.cu).
+// Returns 1 if the sweep is not eligible (the caller then screens with the mean-only panel pass).
+struct CandDesc;
+int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, int64_t c_begin, int64_t c_end, int kind, double explore,
+                      double f_best, double prior_diag, void* d_workspace, size_t workspace_bytes, double* d_f, bogp_result* d_result);
+size_t gemm_screen_f_doubles(const AcqChunk& tab);
 size_t i8_wq_bytes(int64_t n_pad);
 size_t i8_panel_bytes(int64_t n_pad, int64_t S);
 int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp, double* d_wscale, uint8_t* d_wq);

@@ -168,6 +168,11 @@ class GPEngine:
         same winner as the full sweep -- include/bogp.h)."""
         _lib.check(self.lib.bogp_set_screening(self._ctx, 1 if enable else 0))
 
+    def set_fused(self, enable: bool, group: int = 0):
+        """INT8 path: one persistent fused kernel per sweep, or (default) the per-chunk panel / product / finalize / merge
+        kernels; bit-identical outputs (include/bogp.h bogp_set_fused).  `group` = candidate tiles per work group, 0 = automatic."""
+        _lib.check(self.lib.bogp_set_fused(self._ctx, 1 if enable else 0, int(group)))
+
     def screen_stats(self, reset: bool = True):
         """(candidates screened, survivors) since the last reset."""
         a, b = C.c_int64(), C.c_int64()

@@ -86,6 +86,11 @@ class Session:
         for i in range(len(self.devices)):
             _lib.check(self.lib.bogp_set_screening(C.c_void_p(self.lib.bogp_session_ctx(self._h, i)), 1 if enable else 0))
 
+    def set_fused(self, enable: bool, group: int = 0):
+        """One persistent fused kernel per sweep, or (default) the separate kernels, per device context (include/bogp.h)."""
+        for i in range(len(self.devices)):
+            _lib.check(self.lib.bogp_set_fused(C.c_void_p(self.lib.bogp_session_ctx(self._h, i)), 1 if enable else 0, int(group)))
+
     # ------------------------------------------------------------------ point_selector.py:166-195
     def kernel_matrix(self, a, b, ell, jitter: float = 0.0) -> np.ndarray:
         a, b = _f64(a), _f64(b)

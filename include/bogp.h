@@ -72,6 +72,14 @@ int bogp_get_acquire_path(const bogp_ctx* ctx);
  * (score, index) is the one of the unscreened sweep (csrc/acquire.cu, screen_kernel).  0 switches it off.          */
 int bogp_set_screening(bogp_ctx* ctx, int enable);
 int bogp_get_screening(const bogp_ctx* ctx);
+/* INT8 path: run a sweep as ONE persistent fused kernel (enable = 1) -- grid index -> k_* digits -> tcgen05 product ->
+ * sigma^2, mu -> acquisition -> max-loc, the k_* panel living only in an L2-sized ring (csrc/acquire_fused.cu; no k_*
+ * traffic to HBM, a 60 MB workspace instead of 2 GB) -- or (enable = 0, the default: measured ~6 % faster at N = 4096
+ * because the panel kernel already overlaps the product on a second stream) as per-chunk panel / product / finalize /
+ * merge kernels.  Outputs are bit-identical either way.
+ * `group` = candidate tiles per work group of the fused kernel, 0 = automatic.  Replaces point_selector.py:81,90-98,204-207. */
+int bogp_set_fused(bogp_ctx* ctx, int enable, int group);
+int bogp_get_fused(const bogp_ctx* ctx);
 /* candidates that went through the screen / that survived it since the last reset (synchronises the stream) */
 int bogp_screen_stats(bogp_ctx* ctx, int64_t* h_screened, int64_t* h_survived, int reset);
 /* Measurement aid: when enabled, each kernel of the acquisition sweep is bracketed by CUDA

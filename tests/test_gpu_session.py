@@ -45,8 +45,10 @@ def test_session_update_is_bit_identical_to_the_device_resident_path(path):
     axes = [np.linspace(0, 1, 7)] * 5
     P = o.candidate_grid(axes)
     fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
-    ref = eng.acquire(fit, CandidateGrid(axes), outputs=True)
+    # the session against the device-resident engine on the same kind of candidates (a grid descriptor and an explicit array
+    # of the same points differ by a few ulp of k_* on the INT8 path: per-axis factor tables, csrc/acquire_i8.cuh)
     for kw in (dict(points=P), dict(axes=axes)):
+        ref = eng.acquire(fit, CandidateGrid(axes) if "axes" in kw else P, outputs=True)
         got = s.update(X, y, ell, want_acq=True, **kw)
         np.testing.assert_array_equal(got["mu"], ref.mu.cpu().numpy())
         np.testing.assert_array_equal(got["sigma"], ref.sigma.cpu().numpy())
