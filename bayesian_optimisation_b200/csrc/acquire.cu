@@ -475,7 +475,6 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
     const bool use_i8 = ctx->acquire_path == BOGP_PATH_INT8_TCGEN05 && n_pad <= 16384;
     // Grid sweeps on the INT8 path: per-axis kernel-factor tables, built once per sweep into the tail of the workspace
     AcqChunk tab{};
-    double* gemm_f = nullptr;
     if (use_i8 && !cd.points) {
         tab.axes = cd.axes; tab.x_pad = fit_xpad(fit); tab.inv_ell2 = fit_inv_ell2(fit); tab.dim = dim; tab.n_pad = (int)n_pad;
         for (int k = 0; k < BOGP_MAX_DIM; k++) { tab.len[k] = cd.len[k]; tab.off[k] = cd.off[k]; }
@@ -486,12 +485,6 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
             tab.ft = reinterpret_cast<const double*>(static_cast<char*>(d_workspace) + workspace_bytes);
             const int trc = launch_grid_factors(ctx, tab, const_cast<double*>(tab.ft), ctx->stream);
             if (trc) return trc;
-            // the F operand of the mean GEMM of a screened sweep (screen_gemm.cu) sits below the tables
-            const size_t fb = (gemm_screen_f_doubles(tab) * 8 + 255) / 256 * 256;
-            if (fb > 0 && tb + fb <= grid_table_reserve(n_pad) && workspace_bytes - fb >= acq_layout(n_pad, kAcqBN).total) {
-                workspace_bytes -= fb;
-                gemm_f = reinterpret_cast<double*>(static_cast<char*>(d_workspace) + workspace_bytes);
-            }
         }
     }
     // chunk capacity from the workspace size
@@ -539,9 +532,9 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         if (fused_rc) return fused_rc;
     }
     if (fused_done) return BOGP_OK;
-    if (screen && gemm_f) {
+    if (screen && tab.ft) {
         // grid sweep: the means of all candidates from GEMMs, survivors scored exactly (screen_gemm.cu)
-        const int grc = gemm_screen_sweep(ctx, fit, tab, c_begin, c_end, kind, explore, f_best, prior_diag, d_workspace, workspace_bytes, gemm_f, d_result);
+        const int grc = gemm_screen_sweep(ctx, fit, tab, c_begin, c_end, kind, explore, f_best, prior_diag, d_workspace, workspace_bytes, d_result);
         if (grc != 1) return grc;
     }
     init_best_kernel<<<1, 1, 0, st>>>(best, besti, nan_flag); BOGP_LAUNCH_CHECK(ctx);

@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(256) grid_factor_kernel(GridTabArgs a) {
 }
 
 size_t grid_table_reserve(int64_t n_pad) {
-    const size_t full = (size_t)n_pad * BOGP_MAX_DIM * 64 * 8;      // tables (both layouts) ...
-    return (full < ((size_t)64 << 20) ? full : ((size_t)64 << 20)) + (size_t)n_pad * 256 * 8 + 4096;   // ... + the F operand of the mean GEMM
+    const size_t full = (size_t)n_pad * BOGP_MAX_DIM * 64 * 8;      // tables, both layouts
+    return full < ((size_t)64 << 20) ? full : ((size_t)64 << 20);
 }
 
 size_t grid_table_geometry(AcqChunk& a) {

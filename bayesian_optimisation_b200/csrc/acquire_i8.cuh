@@ -190,6 +190,8 @@ __device__ __forceinline__ double panel_rows(const PanelRowCtx& c, const SRC& sr
     return mu;
 }
 
+static __device__ const double kOneTab[1] = {1.0};
+
 template <int DIMP>
 struct PanelSmem {
     alignas(128) double ps_raw[kI8BN * BOGP_MAX_DIM];   // candidate block, [cand][dim] as in HBM
@@ -256,11 +258,16 @@ __device__ __forceinline__ bool panel_tile_table(const PanelI8Args& p, int64_t c
     const int last = nvalid - 1;
     {   // prefix products over the leading axes, (((1 f_0) f_1) ... f_{kl-1}), for the settings of the first and the last candidate
         const int64_t j = (int64_t)jb * kAcqBM + tid;
-        double v0 = 1.0, v1 = 1.0;
-        for (int k = 0; k < kl; k++) {
-            const double* row = p.cand.ft + p.cand.toff[k] + j * p.cand.lenp[k];
-            v0 *= __ldg(row + dg[k]); v1 *= __ldg(row + dg[last * BOGP_MAX_DIM + k]);
+        double f0[DIMP], f1[DIMP];
+#pragma unroll
+        for (int k = 0; k < DIMP; k++) {           // all loads in flight together
+            const bool lead = k < kl;
+            const double* row = p.cand.ft + (lead ? p.cand.toff[k] + j * p.cand.lenp[k] : 0);
+            f0[k] = lead ? __ldg(row + dg[k]) : 1.0; f1[k] = lead ? __ldg(row + dg[last * BOGP_MAX_DIM + k]) : 1.0;
         }
+        double v0 = 1.0, v1 = 1.0;
+#pragma unroll
+        for (int k = 0; k < DIMP; k++) { v0 *= f0[k]; v1 *= f1[k]; }      // x 1.0 is exact
         sm.pre[0][tid] = v0; sm.pre[1][tid] = v1;
     }
     const int nl = tid & 63;
@@ -294,11 +301,16 @@ __device__ __forceinline__ bool panel_tile_table(const PanelI8Args& p, int64_t c
 // Table mode for candidates scattered over the grid (the compacted survivors of a screened sweep): the same ordered product
 // (((1 f_0) f_1) ... f_{d-1}) with every factor read from the tables in L2 -- the same bits as panel_tile_table gives the
 // candidate inside a contiguous sweep, at the price of d dependent-latency loads per entry (survivors are few).
+template <int DIMP>
 struct TabSrcAll {
-    const double* tp[BOGP_MAX_DIM]; int stride[BOGP_MAX_DIM]; int dim;
+    const double* tp[DIMP]; int stride[DIMP];      // axes beyond the real dimension point at a constant 1.0 (stride 0)
     __device__ __forceinline__ double eval(int jl) const {
+        double f[DIMP];
+#pragma unroll
+        for (int k = 0; k < DIMP; k++) f[k] = __ldg(tp[k] + (int64_t)jl * stride[k]);      // all loads in flight together
         double v = 1.0;
-        for (int k = 0; k < dim; k++) v *= __ldg(tp[k] + (int64_t)jl * stride[k]);
+#pragma unroll
+        for (int k = 0; k < DIMP; k++) v *= f[k];                                          // x 1.0 is exact
         return v;
     }
 };
@@ -308,10 +320,12 @@ __device__ __forceinline__ bool panel_tile_scattered(const PanelI8Args& p, int64
     const int* dg = reinterpret_cast<const int*>(sm.ps_raw);
     const int nl = tid & 63;
     const int ncl = nl < nvalid ? nl : nvalid - 1;
-    TabSrcAll src; src.dim = p.dim;
-    for (int k = 0; k < p.dim; k++) {
-        src.stride[k] = p.cand.lenp[k];
-        src.tp[k] = p.cand.ft + p.cand.toff[k] + (int64_t)jb * kAcqBM * p.cand.lenp[k] + dg[ncl * BOGP_MAX_DIM + k];
+    TabSrcAll<DIMP> src;
+#pragma unroll
+    for (int k = 0; k < DIMP; k++) {
+        const bool real = k < p.dim;
+        src.stride[k] = real ? p.cand.lenp[k] : 0;
+        src.tp[k] = real ? p.cand.ft + p.cand.toff[k] + (int64_t)jb * kAcqBM * p.cand.lenp[k] + dg[ncl * BOGP_MAX_DIM + k] : kOneTab;
     }
     PanelRowCtx rc;
     rc.al = sm.al;

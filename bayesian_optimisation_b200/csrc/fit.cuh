@@ -59,8 +59,7 @@ size_t grid_table_reserve(int64_t n_pad);
 // Returns 1 if the sweep is not eligible (the caller then screens with the mean-only panel pass).
 struct CandDesc;
 int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, int64_t c_begin, int64_t c_end, int kind, double explore,
-                      double f_best, double prior_diag, void* d_workspace, size_t workspace_bytes, double* d_f, bogp_result* d_result);
-size_t gemm_screen_f_doubles(const AcqChunk& tab);
+                      double f_best, double prior_diag, void* d_workspace, size_t workspace_bytes, bogp_result* d_result);
 size_t i8_wq_bytes(int64_t n_pad);
 size_t i8_panel_bytes(int64_t n_pad, int64_t S);
 int launch_slice_w(bogp_ctx* ctx, const double* d_w, int64_t n_pad, int* d_wexp, double* d_wscale, uint8_t* d_wq);

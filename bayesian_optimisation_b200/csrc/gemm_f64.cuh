@@ -13,7 +13,15 @@
 namespace bogp {
 
 enum GemmBLayout { B_NK = 0 /* B is N x K row-major: C = A * B^T */, B_KN = 1 /* B is K x N row-major */ };
-enum GemmALayout { A_MK = 0 /* A is M x K row-major */, A_KM = 1 /* A is K x M row-major: C = A^T * B */ };
+enum GemmALayout { A_MK = 0 /* A is M x K row-major */, A_KM = 1 /* A is K x M row-major: C = A^T * B */,
+                   A_GEN = 2 /* A[m, k] is not stored: it is the ordered product of per-axis table rows (GemmGenA) */ };
+
+// Generated A operand (screen_gemm.cu): row m stands for setting p0 + m of the leading grid axes, A[m, k] =
+// (((1 f_0[k]) f_1[k]) ... f_{kl-1}[k]) with f_a = table row tab[toff[a] + digit_a(m) * ld + k].  The digits of the tile's
+// rows are expected as 16-bit values at smem + GemmSmem::bytes, [BM][16] (the calling kernel puts them there).
+struct GemmGenA {
+    const double* tab; int toff[16]; int kl; int64_t ld;
+};
 enum GemmKRange  { K_ALL = 0, K_GE_N = 1 /* B[k,n] == 0 for k < n */, K_LE_M = 2 /* A[m,k] == 0 for k > m */,
                    K_GE_MAXMN = 3 /* A^T*B with both lower triangular: k >= max(m, n) */ };
 
@@ -27,6 +35,7 @@ struct GemmArgs {
     double alpha;
     int accumulate;     // C += ...
     int lower_only;     // only tiles / elements with row >= col are produced (SYRK)
+    const GemmGenA* gen; // A_GEN only (device pointer)
 };
 
 constexpr int GK = 32;          // k extent per stage
@@ -73,7 +82,21 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& g, const double* A, co
         const int k0 = kbeg + kt * GK;
         double* a = sA + stage * S::kAStage;
         double* b = sB + stage * S::kBStage;
-        if (AL == A_MK) {      // [BM][GPADK], 8 chunks of 16 B per row
+        if (AL == A_GEN) {     // [BM][GPADK]: every thread forms 2 consecutive k of BM / 16 rows from the table rows (L1 / L2 resident)
+            const unsigned short* dg = reinterpret_cast<const unsigned short*>(smem + S::bytes / sizeof(double));
+            const GemmGenA& ga = *g.gen;
+            for (int c = tid; c < BM * (GK / 2); c += 256) {
+                const int r = c / (GK / 2), q = c % (GK / 2);
+                double2 v = make_double2(1.0, 1.0);
+                const int64_t kq = k0 + q * 2;
+                for (int ax = 0; ax < ga.kl; ax++) {
+                    const double2 f = __ldg(reinterpret_cast<const double2*>(ga.tab + ga.toff[ax] + (int64_t)dg[r * 16 + ax] * ga.ld + kq));
+                    v.x *= f.x; v.y *= f.y;
+                }
+                if (m0 + r >= g.M || kq >= kend) v = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(a + r * GPADK + q * 2) = v;
+            }
+        } else if (AL == A_MK) {      // [BM][GPADK], 8 chunks of 16 B per row
             for (int c = tid; c < BM * (GK / 2); c += 256) {
                 int r = c / (GK / 2), q = c % (GK / 2);
                 bool ok = (m0 + r < g.M) && (k0 + q * 2 < kend);
@@ -128,7 +151,7 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& g, const double* A, co
 #pragma unroll
             for (int i = 0; i < MI; i++) {
                 int r = wm * WM + i * 8 + lr;
-                af[i] = (AL == A_MK) ? a[r * GPADK + kk * 4 + lk] : a[(kk * 4 + lk) * (BM + 4) + r];
+                af[i] = (AL != A_KM) ? a[r * GPADK + kk * 4 + lk] : a[(kk * 4 + lk) * (BM + 4) + r];
             }
 #pragma unroll
             for (int j = 0; j < NI; j++) {

@@ -8,7 +8,8 @@
 //      mu[p, t] = sum_j G[p, j] F[t, j],     G[p, j] = prod_{leading k} f_k[j, p_k],   F[t, j] = alpha_j prod_{trailing k} f_k[j, t_k]
 //
 // is a plain matrix product (P x N) (N x T): ONE multiply-add per (candidate, measurement) on the FP64 tensor path instead
-// of a squared distance, an exp and a multiply-add -- 27 ms instead of 1.1 s for the 10^8-point grid at N = 4096.
+// of a squared distance, an exp and a multiply-add.  G is never stored: the GEMM forms its A tiles on the fly from the
+// table rows (gemm_f64.cuh, A_GEN), 2 (kl - 1) multiplications per 32 x BN multiply-adds.
 //
 // The GEMM's mu differs from the mu of the exact kernels by rounding only (different association and summation order):
 // |mu_gemm - mu_exact| <= (2 n_pad + 16) u sum_j |alpha_j| k_j <= eps := (2 n_pad + 16) 2^-53 1.0002 |alpha|_1, so the screen
@@ -24,32 +25,55 @@
 namespace bogp {
 
 constexpr int kGsSeed = 4096;            // candidates of the strided seed sample scored before the first chunk
+constexpr int kGsBatch = 4;              // chunks whose survivors are scored together by one exact pass
 
 struct GsGeom {
     const double* ft; int toffT[BOGP_MAX_DIM]; int len[BOGP_MAX_DIM];
     int dim, kl, n, n_pad; long long ttot;
 };
 
-// F[t, j] = alpha_j * (((1 f_kl) f_kl+1) ...), rows over j.  grid (n_pad / 256, T)
-__global__ void __launch_bounds__(256) gs_fmat_kernel(GsGeom g, const double* __restrict__ alpha, double* __restrict__ F) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    long long t = blockIdx.y;
+// out[r, j] = (alpha_j) * (((1 f_ka) f_ka+1) ... f_kb-1) for setting r of the axes [ka, kb), rows over j.
+// grid (settings, n_pad / 256): F (with alpha) over the trailing axes, G (without) over the leading ones.
+__global__ void __launch_bounds__(256) gs_prod_kernel(GsGeom g, int ka, int kb, const double* __restrict__ alpha, double* __restrict__ out) {
+    const int j = blockIdx.y * 256 + threadIdx.x;
+    long long t = blockIdx.x;
     int dig[BOGP_MAX_DIM];
-    for (int k = g.dim - 1; k >= g.kl; k--) { dig[k] = (int)(t % g.len[k]); t /= g.len[k]; }
+    for (int k = kb - 1; k >= ka; k--) { dig[k] = (int)(t % g.len[k]); t /= g.len[k]; }
     double v = 1.0;
-    for (int k = g.kl; k < g.dim; k++) v *= g.ft[g.toffT[k] + (int64_t)dig[k] * g.n_pad + j];
-    F[(int64_t)blockIdx.y * g.n_pad + j] = j < g.n ? alpha[j] * v : 0.0;
+    for (int k = ka; k < kb; k++) v *= g.ft[g.toffT[k] + (int64_t)dig[k] * g.n_pad + j];
+    if (alpha) v = j < g.n ? alpha[j] * v : 0.0;
+    out[(int64_t)blockIdx.x * g.n_pad + j] = v;
 }
 
-// G[p - p0, j] = (((1 f_0) f_1) ... f_kl-1), rows over j.  grid (n_pad / 256, prefixes of the chunk)
-__global__ void __launch_bounds__(256) gs_gmat_kernel(GsGeom g, long long p0, double* __restrict__ G) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    long long p = p0 + blockIdx.y;
-    int dig[BOGP_MAX_DIM];
-    for (int k = g.kl - 1; k >= 0; k--) { dig[k] = (int)(p % g.len[k]); p /= g.len[k]; }
-    double v = 1.0;
-    for (int k = 0; k < g.kl; k++) v *= g.ft[g.toffT[k] + (int64_t)dig[k] * g.n_pad + j];
-    G[(int64_t)blockIdx.y * g.n_pad + j] = v;
+// mu[p - p0, t] = sum_j G[p, j] F[t, j] with G generated on the fly (gemm_f64.cuh, A_GEN): G[p, j] = (((1 f_0) f_1) ... f_kl-1)
+// from the transposed table rows, never stored.  grid (ceil(T / BN), ceil(prefixes / 128)), 256 threads.
+template <int BN>
+__global__ void __launch_bounds__(256) gs_mu_gemm_kernel(GemmArgs g, GemmGenA gen, GsGeom geo, long long p0) {
+    extern __shared__ __align__(16) double smem[];
+    using S = GemmSmem<128, BN>;
+    unsigned short* dg = reinterpret_cast<unsigned short*>(smem + S::bytes / sizeof(double));
+    const int m0 = blockIdx.y * 128;
+    if (threadIdx.x < 128) {
+        long long p = p0 + m0 + threadIdx.x;
+        for (int k = geo.kl - 1; k >= 0; k--) { dg[threadIdx.x * 16 + k] = (unsigned short)(p % geo.len[k]); p /= geo.len[k]; }
+    }
+    __syncthreads();
+    GemmArgs gg = g;
+    gg.gen = &gen;
+    gemm_tile<128, BN, A_GEN, B_NK, K_ALL>(gg, nullptr, g.B, g.C, m0, blockIdx.x * BN, smem);
+}
+
+template <int BN>
+static int launch_mu_gemm(bogp_ctx* ctx, const GemmArgs& m, const GemmGenA& gen, const GsGeom& geo, long long p0) {
+    static DeviceOnce configured;
+    constexpr size_t smem = GemmSmem<128, BN>::bytes + 128 * 16 * 2;
+    if (configured.need(ctx->device)) {
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(gs_mu_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BOGP_CUDA_CHECK(cudaFuncSetAttribute(gs_mu_gemm_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    gs_mu_gemm_kernel<BN><<<dim3((m.N + BN - 1) / BN, (m.M + 127) / 128), 256, smem, ctx->stream>>>(m, gen, geo, p0);
+    BOGP_LAUNCH_CHECK(ctx);
+    return BOGP_OK;
 }
 
 __global__ void __launch_bounds__(256) gs_alpha_l1_kernel(const double* __restrict__ alpha, int n, double* __restrict__ out) {
@@ -108,43 +132,105 @@ static bool gs_geometry(const AcqChunk& tab, GsGeom& g) {
     for (int k = 0; k < BOGP_MAX_DIM; k++) { g.toffT[k] = tab.toffT[k]; g.len[k] = tab.len[k]; }
     for (int k = g.kl; k < g.dim; k++) t *= tab.len[k];
     g.ttot = t;
-    return t >= 1 && t <= 256;
-}
-
-size_t gemm_screen_f_doubles(const AcqChunk& tab) {
-    GsGeom g{};
-    return gs_geometry(tab, g) ? (size_t)g.ttot * tab.n_pad : 0;
+    if (tab.dim < 2) return false;
+    for (int k = 0; k < tab.dim; k++) if (tab.len[k] > 65535) return false;  // digits travel as 16-bit values
+    return true;
 }
 
 int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, int64_t c_begin, int64_t c_end, int kind, double explore,
-                      double f_best, double prior_diag, void* d_workspace, size_t workspace_bytes, double* d_f, bogp_result* d_result) {
+                      double f_best, double prior_diag, void* d_workspace, size_t workspace_bytes, bogp_result* d_result) {
     GsGeom g{};
-    if (!d_f || !gs_geometry(tab, g)) return 1;
+    if (!gs_geometry(tab, g)) return 1;
     const int64_t n_pad = tab.n_pad;
-    const long long T = g.ttot;
-    const int ldc = (int)(T + (T & 1));                            // even row stride: the GEMM stores pairs
-    // workspace: [ring of the fused exact pass][G chunk][mu chunk][survivor indices][count]
+    // workspace: [ring of the fused exact pass][stored operands G, F (stored mode)][mu chunk][survivor indices of a batch of chunks][count]
     const size_t ring = (fused_workspace_bytes(n_pad) + 255) / 256 * 256;
     if (workspace_bytes < ring + ((size_t)1 << 20)) return 1;
     const size_t avail = workspace_bytes - ring - 4096;
-    const size_t per_prefix = (size_t)n_pad * 8 + (size_t)ldc * 8 + (size_t)T * 8;
-    long long Pc = (long long)128 * ctx->sm_count;
-    if ((size_t)Pc * per_prefix > avail) Pc = (long long)(avail / per_prefix);
-    if (Pc > 65535) Pc = 65535;
-    Pc = Pc / 128 * 128;
-    if (Pc < 128) return 1;
+
+    // Split of the axes for the GEMM, c = p * T + t.  Stored mode: the split that minimises the two operand matrices
+    // G (settings of the leading axes x N) and F (settings of the trailing axes x N), both built once per sweep -- a plain
+    // GEMM with stored operands, if they fit half of the workspace.  Otherwise generated mode: the trailing axes of the
+    // factor tables (T <= 256, F in the table reserve), G formed tile by tile inside the GEMM.
+    int ks = 0; long long Ps = 0, Ts = 0;
+    {
+        long long tot = 1;
+        for (int k = 0; k < g.dim; k++) tot *= g.len[k];
+        long long P = 1, bestsum = -1;
+        for (int k = 1; k < g.dim; k++) {
+            P *= g.len[k - 1];
+            const long long Tk = tot / P;
+            if (Tk > 0x7fffffffLL || P > 0x7fffffffLL) continue;
+            if (bestsum < 0 || P + Tk < bestsum) { bestsum = P + Tk; ks = k; Ps = P; Ts = Tk; }
+        }
+        if (bestsum < 0 || (size_t)bestsum * n_pad * 8 > avail / 2) ks = 0;
+    }
+    const bool stored = ks > 0;
+    // generated mode: as many trailing axes as keep T <= 1024 columns (full 128-column tiles, F of a few tens of MB)
+    int kg = g.dim - 1; long long Tg = g.len[g.dim - 1];
+    while (kg > 1 && Tg * g.len[kg - 1] <= 1024) { kg--; Tg *= g.len[kg]; }
+    const long long T = stored ? Ts : Tg;
+    const int kl = stored ? ks : kg;
+    const int ldc = (int)(T + (T & 1));                            // even row stride: the GEMM stores pairs
     char* base = static_cast<char*>(d_workspace);
-    double* G = reinterpret_cast<double*>(base + ring);
-    double* mu = G + (size_t)Pc * n_pad;
+    double* Gs = reinterpret_cast<double*>(base + ring);
+    double* Fs = stored ? Gs + (size_t)Ps * n_pad : Gs;
+    if (((size_t)(stored ? Ps : 0) + (size_t)T) * n_pad * 8 + ((size_t)1 << 20) > avail) return 1;
+    char* rest = reinterpret_cast<char*>(Fs + (size_t)T * n_pad);
+    const size_t rest_bytes = avail - (size_t)(rest - (base + ring));
+    // Generated mode: the leading axes are folded into TWO composite axes whose product rows are stored (C1 over the
+    // axes [0, ka), C2 over [ka, kl)), so a generated A element costs two loads and one multiplication whatever kl is.
+    // If the composite tables do not fit, the per-axis table rows are used directly (kl loads per element).
+    GemmGenA gen{};
+    GsGeom gg = g; gg.kl = kl;
+    gen.tab = g.ft; gen.kl = kl; gen.ld = n_pad;
+    for (int k = 0; k < 16; k++) gen.toff[k] = g.toffT[k];
+    int ka = 0; long long P1 = 0, P2 = 0;
+    if (!stored && kl >= 2) {
+        long long tot = 1;
+        for (int k = 0; k < kl; k++) tot *= g.len[k];
+        long long P = 1, bestsum = -1;
+        for (int k = 1; k < kl; k++) {
+            P *= g.len[k - 1];
+            if (P > 65535 || tot / P > 65535) continue;
+            if (bestsum < 0 || P + tot / P < bestsum) { bestsum = P + tot / P; ka = k; P1 = P; P2 = tot / P; }
+        }
+        if (bestsum < 0 || (size_t)bestsum * n_pad * 8 > rest_bytes / 2 || (size_t)P1 * n_pad > 0x7fffffffULL) ka = 0;
+    }
+    double* comp = reinterpret_cast<double*>(rest);
+    size_t comp_bytes = 0;
+    if (ka > 0) {
+        comp_bytes = ((size_t)(P1 + P2) * n_pad * 8 + 255) / 256 * 256;
+        gen.tab = comp; gen.kl = 2; gen.toff[0] = 0; gen.toff[1] = (int)((size_t)P1 * n_pad);
+        gg.kl = 2; gg.len[0] = (int)P1; gg.len[1] = (int)P2;
+    }
+    // rows (settings of the leading axes) per chunk: at least ~2.5 M candidates, and a number of 128-row tiles that fills
+    // whole waves of the SMs (the smallest row count with >= 88 % of the last wave used, else the best one that fits)
+    const size_t per_row = (size_t)ldc * 8 + (size_t)kGsBatch * T * 8;
+    const long long col_tiles = (T + (T <= 64 ? 63 : 127)) / (T <= 64 ? 64 : 128);
+    long long Pc = 128; double beste = 0.0;
+    for (long long r = 1; r <= 1024; r++) {
+        if ((size_t)(r * 128) * per_row > rest_bytes - comp_bytes) break;
+        const long long tiles = r * col_tiles, waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
+        const double e = (double)tiles / (double)(waves * ctx->sm_count);
+        if (e > beste + 1e-9) { beste = e; Pc = r * 128; }
+        if (e >= 0.88 && r * 128 * T >= 2500000) { Pc = r * 128; break; }
+    }
+    if ((size_t)Pc * per_row > rest_bytes - comp_bytes) return 1;
+    double* mu = reinterpret_cast<double*>(rest + comp_bytes);
     long long* surv = reinterpret_cast<long long*>(mu + (size_t)Pc * ldc);
-    int* count = reinterpret_cast<int*>(surv + (size_t)Pc * T);
-    const long long cap = Pc * T;                                  // survivors of a chunk: at most all of its candidates
-    if ((size_t)(reinterpret_cast<char*>(count) - base) + 256 > workspace_bytes || cap < kGsSeed) return 1;
+    int* count = reinterpret_cast<int*>(surv + (size_t)kGsBatch * Pc * T);
+    const long long cap = kGsBatch * Pc * T;                       // survivors of a batch of chunks: at most all of their candidates
+    if (cap < kGsSeed) return 1;
 
     cudaStream_t st = ctx->stream;
     double* l1 = ctx->d_scalars + 20;
     gs_alpha_l1_kernel<<<1, 256, 0, st>>>(fit_alpha(fit), (int)fit_n(fit), l1); BOGP_LAUNCH_CHECK(ctx);
-    gs_fmat_kernel<<<dim3((unsigned)(n_pad / 256), (unsigned)T), 256, 0, st>>>(g, fit_alpha(fit), d_f); BOGP_LAUNCH_CHECK(ctx);
+    gs_prod_kernel<<<dim3((unsigned)T, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, kl, g.dim, fit_alpha(fit), Fs); BOGP_LAUNCH_CHECK(ctx);
+    if (stored) { gs_prod_kernel<<<dim3((unsigned)Ps, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, 0, kl, nullptr, Gs); BOGP_LAUNCH_CHECK(ctx); }
+    if (ka > 0) {
+        gs_prod_kernel<<<dim3((unsigned)P1, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, 0, ka, nullptr, comp); BOGP_LAUNCH_CHECK(ctx);
+        gs_prod_kernel<<<dim3((unsigned)P2, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, ka, kl, nullptr, comp + (size_t)P1 * n_pad); BOGP_LAUNCH_CHECK(ctx);
+    }
 
     // exact scoring of the candidates listed in surv[0 .. *count): one launch of the fused persistent kernel
     auto exact_pass = [&](int fold) -> int {
@@ -172,21 +258,38 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
     sa.best = d_result; sa.surv_idx = surv; sa.count = count;
     sa.stats = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 16);
     const long long p_begin = c_begin / T, p_end = (c_end + T - 1) / T;
+    int pending = 0;                                               // whole chunks screened since the last exact pass
+    long long sub_rows = (250000 + T - 1) / T;                     // rows per screened range, doubling
+    BOGP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
     for (long long p0 = p_begin; p0 < p_end; p0 += Pc) {
         const long long pc = (p_end - p0 < Pc) ? (p_end - p0) : Pc;
-        gs_gmat_kernel<<<dim3((unsigned)(n_pad / 256), (unsigned)pc), 256, 0, st>>>(g, p0, G); BOGP_LAUNCH_CHECK(ctx);
         GemmArgs m{};
-        m.A = G; m.lda = n_pad; m.B = d_f; m.ldb = n_pad; m.C = mu; m.ldc = ldc;
+        m.A = stored ? Gs + (size_t)p0 * n_pad : nullptr; m.lda = n_pad; m.B = Fs; m.ldb = n_pad; m.C = mu; m.ldc = ldc;
         m.M = (int)pc; m.N = (int)T; m.K = (int)n_pad; m.alpha = 1.0; m.accumulate = 0; m.lower_only = 0;
-        rc = (T <= 64) ? launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, m, 1) : launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, m, 1);
+        if (stored)       rc = (T <= 64) ? launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, m, 1) : launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, m, 1);
+        else if (T <= 64) rc = launch_mu_gemm<64>(ctx, m, gen, gg, p0);
+        else              rc = launch_mu_gemm<128>(ctx, m, gen, gg, p0);
         if (rc) return rc;
-        BOGP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
         sa.base = p0 * T;
-        sa.lo = sa.base > c_begin ? sa.base : c_begin;
-        sa.hi = (p0 + pc) * T < c_end ? (p0 + pc) * T : c_end;
-        if (sa.hi > sa.lo) {
-            gs_screen_kernel<<<(unsigned)((sa.hi - sa.lo + 255) / 256), 256, 0, st>>>(sa); BOGP_LAUNCH_CHECK(ctx);
-            rc = exact_pass(1); if (rc) return rc;
+        // The chunk's candidates are screened in row ranges, each followed by the exact scoring of its survivors.  The running
+        // best rises fastest at the beginning, so the ranges start small (~250 k candidates) and double after every exact pass
+        // (which has a fixed cost of ~0.25 ms, the chain of the heaviest row block) until they cover whole chunks; then
+        // kGsBatch chunks share one pass.
+        for (long long r0 = 0; r0 < pc;) {
+            const long long rows = (sub_rows < pc - r0) ? sub_rows : (pc - r0);
+            sa.lo = sa.base + r0 * T > c_begin ? sa.base + r0 * T : c_begin;
+            sa.hi = sa.base + (r0 + rows) * T < c_end ? sa.base + (r0 + rows) * T : c_end;
+            if (sa.hi > sa.lo) { gs_screen_kernel<<<(unsigned)((sa.hi - sa.lo + 255) / 256), 256, 0, st>>>(sa); BOGP_LAUNCH_CHECK(ctx); }
+            r0 += rows;
+            const bool last = (r0 >= pc) && (p0 + Pc >= p_end);
+            bool pass = last;
+            if (sub_rows < Pc) { pass = true; sub_rows *= 2; }                     // still ramping up
+            else if (r0 >= pc && ++pending == kGsBatch) pass = true;
+            if (pass) {
+                rc = exact_pass(1); if (rc) return rc;
+                BOGP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
+                pending = 0;
+            }
         }
     }
     return BOGP_OK;

@@ -299,6 +299,23 @@ def run_gpu_arm(args):
     barrier()
     lcb_value = step_total * 2 / (max_over_ranks(a0.elapsed_time(a1)) * 1e-3)
 
+    # ---- the same steps with each sweep as ONE persistent fused kernel (csrc/acquire_fused.cu): bit-identical results, no k_*
+    #      traffic to HBM; reported beside the headline, which uses the (faster) two-stream pipeline of separate kernels
+    eng.set_fused(True)
+    fz_last = device_step(0)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(2):
+        fz_last = device_step(args.warmup + args.steps - 2 + k)
+    f1.record()
+    barrier()
+    fused_value = step_total * 2 / (max_over_ranks(f0.elapsed_time(f1)) * 1e-3)
+    eng.set_fused(False)
+    fused = {"value": fused_value, "unit": UNIT, "same_winner_as_separate_kernels": bool(fz_last == last),
+             "what": "every sweep as one launch of the persistent fused kernel (grid index -> k_* digits -> tcgen05 product -> sigma^2, mu -> EI -> "
+                     "max-loc; k_* only in an L2-resident ring); include/bogp.h bogp_set_fused"}
+
     # ---- the same steps with the screen the library applies by default to arg-max-only sweeps: identical winner, only the
     #      candidates whose posterior-mean bound reaches the best exact score so far go through the N^2 product
     eng.set_screening(True)
@@ -315,8 +332,9 @@ def run_gpu_arm(args):
     n_scr, n_surv = eng.screen_stats()
     screened = {"value": screened_value, "unit": UNIT, "survivor_fraction_rank0": (n_surv / n_scr) if n_scr else None,
                 "same_winner_as_full_sweep": bool(scr_last == last),
-                "what": "arg-max-only sweep with the posterior-mean screen (include/bogp.h bogp_set_screening): exact (score, index), "
-                        "the N^2 product only for candidates whose bound A(mu, sqrt(prior)) reaches the running best"}
+                "what": "arg-max-only sweep with the posterior-mean screen (include/bogp.h bogp_set_screening): exact (score, index); the means of "
+                        "all grid candidates come from fp64 GEMMs over per-axis kernel-factor tables (csrc/screen_gemm.cu), the N^2 product runs only "
+                        "for candidates whose bound A(mu - eps, sqrt(prior)) reaches the running best"}
     eng.set_screening(False)
 
     # ---- end to end through the reference-facing class: pageable host numpy in, host numpy out.  Under torchrun every
@@ -426,7 +444,7 @@ def run_gpu_arm(args):
                 "candidates_per_step_per_gpu": cands, "candidates_per_step": step_total,
                 "fit_ms": float(np.median(fits_after)), "fit_ms_best": float(min(fits_before + fits_after)),
                 "fit_ms_before_sweeps_median": float(np.median(fits_before)), "fit_ms_after_sweeps_median": float(np.median(fits_after)),
-                "lcb_candidates_per_s": lcb_value, "argmax_only_screened": screened,
+                "lcb_candidates_per_s": lcb_value, "fused_single_kernel": fused, "argmax_only_screened": screened,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "PointSelector.update_surrogate() + expected_improvement(): pageable host numpy arrays in and out through the "
                                "host-buffer C ABI (bogp_session_*)" + ("; one process per GPU, slices all-gathered, one-record max-loc exchange" if world > 1 else ""),

@@ -108,3 +108,81 @@ def test_the_bound_dominates_the_exact_score(eng):
     record_error("screen bound EI", "max (exact EI - bound) / slack", (gap / (1e-12 * (np.abs(fb - mu) + smax))).max())
     assert np.all(gap <= 1e-12 * (np.abs(fb - mu) + smax))
     fit.close()
+
+
+# ------------------------------------------------------------------ grid sweeps: means from GEMMs (csrc/screen_gemm.cu)
+@pytest.mark.parametrize("n,lens,rng_", [
+    (700, (7, 5, 9, 11), (123, 3400)),            # odd number of trailing settings (padded row stride), range cut inside rows
+    (1200, (6,) * 6, (0, 6 ** 6)),                # balanced 3 + 3 split, stored operands
+    (300, (3, 50, 40), (777, 5999)),              # long axes: no factor tables, the screen falls back to the mean-only panel pass
+    (2100, (4,) * 9, (1000, 260_000)),            # nine axes
+])
+def test_gemm_screen_returns_the_exact_winner_on_ragged_grids_and_ranges(eng, n, lens, rng_):
+    from bayesian_optimisation_b200.engine import ACQ_EI, CandidateGrid, JITTER_POSTERIOR
+    d = len(lens)
+    X, y, ell = o.synthetic_problem(n, d, seed=n)
+    grid = CandidateGrid([np.linspace(0, 1, L) for L in lens])
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    b, e = rng_
+    for kw in (dict(), dict(kind=ACQ_EI, f_best=float(y.min()))):
+        full, scr, screened, survived = _both(eng, fit, grid, b, e, **kw)
+        assert (scr.best_score, scr.best_index) == (full.best_score, full.best_index)
+        assert b <= scr.best_index < e and screened == e - b
+    fit.close()
+
+
+def test_gemm_screen_generated_operand_mode_when_the_stored_operands_do_not_fit(eng):
+    """A small workspace (chunk = 64 candidates) leaves no room for the two stored operand matrices of the balanced split:
+    the GEMM then forms its A tiles from composite table rows (gemm_f64.cuh, A_GEN).  Same winner."""
+    from bayesian_optimisation_b200.engine import ACQ_EI, CandidateGrid, JITTER_POSTERIOR
+    X, y, ell = o.synthetic_problem(1024, 8, seed=8)
+    grid = CandidateGrid([np.linspace(0, 1, 6)] * 8)            # 1.68 M candidates; balanced split 1296 + 1296 rows of 8 KB = 21 MB
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    fb = float(y.min())
+    eng.set_screening(False)
+    full = eng.acquire(fit, grid, kind=ACQ_EI, f_best=fb)
+    eng.set_screening(True)
+    eng._acq_ws = None                                          # force the minimal workspace of this chunk size
+    scr = eng.acquire(fit, grid, kind=ACQ_EI, f_best=fb, chunk=4096)
+    assert (scr.best_score, scr.best_index) == (full.best_score, full.best_index)
+    eng._acq_ws = None
+    fit.close()
+
+
+def test_gemm_screen_exact_tie_between_grid_duplicates_keeps_the_lowest_index(eng):
+    """An axis with a repeated grid value makes pairs of candidates with bit-identical scores: the lower flat index wins,
+    screened or not."""
+    from bayesian_optimisation_b200.engine import CandidateGrid, JITTER_POSTERIOR
+    X, y, ell = o.synthetic_problem(500, 4, seed=12)
+    ax = np.linspace(0, 1, 8)
+    dup = np.concatenate([ax, ax[::-1]])                        # 16 values, every one twice
+    grid = CandidateGrid([dup, ax, ax, dup])
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    full, scr, screened, survived = _both(eng, fit, grid, 0, grid.size)
+    assert (scr.best_score, scr.best_index) == (full.best_score, full.best_index)
+    acq = eng.acquire(fit, grid, outputs=True).acq.cpu().numpy()
+    assert full.best_index == int(np.flatnonzero(acq == acq.max())[0]) and (acq == acq.max()).sum() >= 4
+    fit.close()
+
+
+def test_gemm_mean_slack_covers_the_rounding_difference(eng):
+    """The screen trusts mu_gemm - eps <= mu_exact with eps = (2 n_pad + 16) 2^-53 1.0002 |alpha|_1.  Host check on the
+    device's own numbers: a float64 GEMM of the same factor tables (numpy, another summation order again) against the mu
+    of the exact kernels stays far inside eps."""
+    from bayesian_optimisation_b200.engine import CandidateGrid, JITTER_POSTERIOR
+    n, d, G = 1500, 5, 7
+    X, y, ell = o.synthetic_problem(n, d, seed=14)
+    axes = [np.linspace(0, 1, G)] * d
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    mu = eng.acquire(fit, CandidateGrid(axes), outputs=True).mu.cpu().numpy()
+    alpha = fit.alpha().cpu().numpy()[:n]
+    f = [np.exp(-0.5 * (axes[k][None, :] - X[:, k:k + 1]) ** 2 / ell[k] ** 2) for k in range(d)]      # (n, G) per axis
+    lead = np.einsum("ja,jb,jc->abcj", f[0], f[1], f[2]).reshape(-1, n)
+    trail = np.einsum("j,ja,jb->abj", alpha, f[3], f[4]).reshape(-1, n)
+    mu_gemm = (lead @ trail.T).reshape(-1)
+    n_pad = fit.n_pad
+    eps = (2 * n_pad + 16) * 2.0 ** -53 * 1.0002 * np.abs(alpha).sum()
+    err = np.abs(mu_gemm - mu).max()
+    record_error("gemm screen", "max |mu_gemm - mu_exact| / eps", err / eps, 1.0, note=f"eps = {eps:.2e}, |alpha|_1 = {np.abs(alpha).sum():.3g}")
+    assert err <= eps
+    fit.close()
