@@ -64,6 +64,7 @@ SIGNATURES = {
     "bogp_get_acquire_path": (_i32, [_vp]),
     "bogp_set_screening": (_i32, [_vp, _i32]),
     "bogp_get_screening": (_i32, [_vp]),
+    "bogp_set_global_seed": (_i32, [_vp, _i32]),
     "bogp_set_fused": (_i32, [_vp, _i32, _i32]),
     "bogp_get_fused": (_i32, [_vp]),
     "bogp_screen_stats": (_i32, [_vp, _pi64, _pi64, _i32]),

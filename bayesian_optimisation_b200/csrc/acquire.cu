@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) screen_kernel(ScreenArgs a) {
     bool keep = false;
     long long idx = 0;
     if (cl < a.cur) {
-        idx = a.c0 + cl * a.stride;
+        idx = a.seed ? seed_index((unsigned long long)cl, a.c0, a.stride) : a.c0 + cl * a.stride;      // seed: stride holds the length of the range
         keep = true;
         if (!a.seed) {
             double mu = 0.0;
@@ -578,7 +578,8 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         // seed: a strided sample over the whole range is scored first, so that the running best is already high
         // when the first batch is screened
         BOGP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
-        sa.seed = 1; sa.c0 = c_begin; sa.cur = kScreenSeed; sa.stride = total / kScreenSeed;
+        sa.seed = 1; sa.c0 = ctx->global_seed ? 0 : c_begin; sa.cur = kScreenSeed;
+        sa.stride = ctx->global_seed ? cd.c_total : total;       // length of the sampled range (global seed: one shard of a sharded arg-max, bogp_set_global_seed)
         screen_kernel<<<(unsigned)((sa.cur + 255) / 256), 256, 0, st>>>(sa); BOGP_LAUNCH_CHECK(ctx);
         int rc = exact_pass(kScreenSeed); if (rc) return rc;
         sa.seed = 0; sa.stride = 1;

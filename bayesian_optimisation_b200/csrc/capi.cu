@@ -91,6 +91,12 @@ extern "C" int bogp_set_screening(bogp_ctx* ctx, int enable) {
 }
 extern "C" int bogp_get_screening(const bogp_ctx* ctx) { return ctx ? ctx->screening : -1; }
 
+extern "C" int bogp_set_global_seed(bogp_ctx* ctx, int enable) {
+    if (!ctx) { set_error("bogp_set_global_seed: null context"); return BOGP_ERR_BAD_ARG; }
+    ctx->global_seed = enable ? 1 : 0;
+    return BOGP_OK;
+}
+
 extern "C" int bogp_set_fused(bogp_ctx* ctx, int enable, int group) {
     if (!ctx || group < 0 || group > 64) { set_error("bogp_set_fused: bad argument"); return BOGP_ERR_BAD_ARG; }
     ctx->fused = enable ? 1 : 0;

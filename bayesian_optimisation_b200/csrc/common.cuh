@@ -85,6 +85,7 @@ struct bogp_ctx {
     int          acquire_path;  // 0 = FP64 DMMA, 1 = INT8 digit slices on tcgen05 (bogp_set_acquire_path)
     int          profile;
     int          screening;     // arg-max-only sweeps: screen by the posterior-mean bound, score survivors exactly (bogp_set_screening)
+    int          global_seed;   // screened sweeps: the seed sample spans the WHOLE candidate set, not only [c_begin, c_end) (bogp_set_global_seed)
     int          fused;         // INT8 path: one persistent fused kernel per sweep (default) instead of per-chunk panel / product / finalize / merge kernels
     int          fused_group;   // candidate tiles per work group of the fused kernel (0 = automatic: ~32 MB of panel digits)
     cudaEvent_t  ev[2];
@@ -195,6 +196,13 @@ __device__ __forceinline__ double exp_nonpos(double t, const double* __restrict_
     return t < -708.0 ? 0.0 : res;
 }
 __device__ __forceinline__ double exp_nonpos(double t) { return exp_nonpos(t, kExp2Tab); }
+
+// i-th candidate of the seed sample of a screened sweep over [begin, begin + total): the golden-ratio sequence
+// frac(i * phi) * total.  (A plain stride is a trap on grids: total / 4096 is a power of the radix for the 8^10 grid, and
+// every seed then sits on the face where the trailing coordinates are all 0.)
+__device__ __forceinline__ long long seed_index(unsigned long long i, long long begin, long long total) {
+    return begin + (long long)__umul64hi((i + 1ull) * 0x9E3779B97F4A7C15ull, (unsigned long long)total);
+}
 
 // (score, index) ordering of the reference: larger score wins, ties -> smaller flat index.
 __device__ __forceinline__ bool better(double s, long long i, double bs, long long bi) {

@@ -9,8 +9,10 @@
 //   * n  > 64  : batched Gram build, batched blocked Cholesky (DMMA trailing updates), batched
 //                recursive triangular inverse, K^-1 = W^T W on the tensor path, and a fused
 //                gradient contraction.
-// nlml = 0.5*(y^T K^-1 y + log det K + n log 2pi) with log det = 2 sum log L_ii (the reference's
-// np.log(np.linalg.det(.)) underflows for n >~ 1000).
+// nlml = 0.5*(y^T K^-1 y + log det K + n log 2pi) with log det = 2 sum log L_ii.  Deliberate deviation: the
+// reference's np.log(np.linalg.det(.)) underflows to -inf as soon as det K < 2^-1074 -- with the 1e-4 jitter from about
+// M = 80-90 measured points on its own grids (earlier for long length scales), not only at N >~ 1000 -- and its float32
+// table then selects the first -inf cell; this path selects the true minimiser (tests/test_gpu_configs.py pins both at M = 120).
 // Gradient (extension; jitter not differentiated), with alpha = K^-1 y:
 //   d nlml/d ell_k = -0.5/ell_k^3 * sum_ij (alpha_i alpha_j - K^-1_ij) k_ij (x_ik - x_jk)^2
 #include "common.cuh"

@@ -87,9 +87,9 @@ __global__ void __launch_bounds__(256) gs_alpha_l1_kernel(const double* __restri
     if (threadIdx.x == 0) { for (int w = 1; w < 8; w++) s += ws[w]; out[0] = s; }
 }
 
-__global__ void __launch_bounds__(256) gs_seed_kernel(long long c_begin, long long stride, int count, long long* __restrict__ idx, int* __restrict__ n_out) {
+__global__ void __launch_bounds__(256) gs_seed_kernel(long long c_begin, long long total, int count, long long* __restrict__ idx, int* __restrict__ n_out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < count) idx[i] = c_begin + (long long)i * stride;
+    if (i < count) idx[i] = seed_index((unsigned long long)i, c_begin, total);
     if (i == 0) n_out[0] = count;
 }
 
@@ -244,11 +244,16 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         if (rc == 1) { set_error("bogp_acquire: workspace too small for the exact pass of a screened sweep"); return BOGP_ERR_WORKSPACE; }
         return rc;
     };
-    // seed: a strided sample over the whole range is scored first, so that the running best is already high when the first
+    // seed: a low-discrepancy sample over the whole range is scored first, so that the running best is already high when the first
     // chunk is screened
-    const long long total = c_end - c_begin;
+    // (ctx->global_seed: the sample spans the whole grid -- this sweep is one shard of a sharded arg-max and all shards
+    // then screen against the same floor)
+    long long gtot = 1;
+    for (int k = 0; k < g.dim; k++) gtot *= g.len[k];
+    const long long s_begin = ctx->global_seed ? 0 : c_begin;
+    const long long total = ctx->global_seed ? gtot : c_end - c_begin;
     const int nseed = (int)(total < kGsSeed ? total : kGsSeed);
-    gs_seed_kernel<<<(nseed + 255) / 256, 256, 0, st>>>(c_begin, total / nseed, nseed, surv, count); BOGP_LAUNCH_CHECK(ctx);
+    gs_seed_kernel<<<(nseed + 255) / 256, 256, 0, st>>>(s_begin, total, nseed, surv, count); BOGP_LAUNCH_CHECK(ctx);
     int rc = exact_pass(0); if (rc) return rc;
 
     GsScreenArgs sa{};

@@ -293,6 +293,8 @@ extern "C" int bogp_session_update(bogp_session* s, const double* h_x, const dou
             cd.d_points = static_cast<const double*>(d.cand.p) - p.b * dim;
         }
         bogp_result* res = static_cast<bogp_result*>(d.res.p);
+        // grid sweeps split over devices / pieces: every part screens against the same, global, seed floor
+        U_TRY(bogp_set_global_seed(d.ctx, (grid && !want_out && (g > 1 || p.pieces > 1)) ? 1 : 0));
         for (int k = 0; k < p.pieces; k++) {
             const int64_t b = p.b + k * p.piece, e = std::min(p.e, b + p.piece);
             if (!grid) {
@@ -306,6 +308,7 @@ extern "C" int bogp_session_update(bogp_session* s, const double* h_x, const dou
                                      want_out ? p.sg + o : nullptr, want_out ? p.aq + o : nullptr, d.acqws.p, d.acqws.cap, res + k));
             U_CUDA(cudaEventRecord(d.ev_out[k], d.stream));
         }
+        U_TRY(bogp_set_global_seed(d.ctx, 0));
         U_TRY(bogp_reduce_results(d.ctx, res, p.pieces, res + kMaxPieces, nullptr, nullptr));
     }
     // phase C: outputs back piece by piece (the copy of piece k overlaps the sweep of piece k+1), status, winner

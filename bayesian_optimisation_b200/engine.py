@@ -168,6 +168,11 @@ class GPEngine:
         same winner as the full sweep -- include/bogp.h)."""
         _lib.check(self.lib.bogp_set_screening(self._ctx, 1 if enable else 0))
 
+    def set_global_seed(self, enable: bool):
+        """Screened sweeps of one shard of a sharded arg-max: seed the screen with a strided sample of the WHOLE candidate
+        set, so that every shard screens against the same floor (include/bogp.h bogp_set_global_seed)."""
+        _lib.check(self.lib.bogp_set_global_seed(self._ctx, 1 if enable else 0))
+
     def set_fused(self, enable: bool, group: int = 0):
         """INT8 path: one persistent fused kernel per sweep, or (default) the per-chunk panel / product / finalize / merge
         kernels; bit-identical outputs (include/bogp.h bogp_set_fused).  `group` = candidate tiles per work group, 0 = automatic."""

@@ -166,7 +166,11 @@ def sharded_acquire(engine, fit, candidates, c_total: int, rank: int, world: int
     """Score this rank's slice on its GPU and reduce on the device.  Returns (score, index, local AcquireResult)."""
     b, e = shard_range(c_total, rank, world)
     if e > b:
-        res = engine.acquire(fit, candidates, b, e, sync=False, **kw)
+        engine.set_global_seed(world > 1)      # screened arg-max-only sweeps: every shard screens against the same floor
+        try:
+            res = engine.acquire(fit, candidates, b, e, sync=False, **kw)
+        finally:
+            engine.set_global_seed(False)
         rec = res.record
     else:
         res, rec = None, engine.empty_record()

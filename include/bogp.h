@@ -80,6 +80,12 @@ int bogp_get_screening(const bogp_ctx* ctx);
  * `group` = candidate tiles per work group of the fused kernel, 0 = automatic.  Replaces point_selector.py:81,90-98,204-207. */
 int bogp_set_fused(bogp_ctx* ctx, int enable, int group);
 int bogp_get_fused(const bogp_ctx* ctx);
+/* Screened sweeps of ONE SHARD of a sharded arg-max (select_parameters.py:282-294 spread over several GPUs): with enable = 1
+ * the strided seed sample that is scored before the screen starts spans the WHOLE candidate set [0, c_total) instead of the
+ * shard [c_begin, c_end), so every shard screens against the same, global, floor -- a shard whose own landscape is flat (far
+ * from all measurements: mu -> 0, sigma -> sigma_max) would otherwise have to score everything exactly.  The record the sweep
+ * returns may then point at a seed candidate OUTSIDE the shard; the winner over all shards is unchanged.  Default 0.      */
+int bogp_set_global_seed(bogp_ctx* ctx, int enable);
 /* candidates that went through the screen / that survived it since the last reset (synchronises the stream) */
 int bogp_screen_stats(bogp_ctx* ctx, int64_t* h_screened, int64_t* h_survived, int reset);
 /* Measurement aid: when enabled, each kernel of the acquisition sweep is bracketed by CUDA

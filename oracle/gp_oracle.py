@@ -21,8 +21,9 @@ against scipy and against central finite differences instead.
 Where the literal reference code cannot run at the benchmark sizes the oracle
 uses an algebraically identical restatement and the golden tests prove the two
 agree wherever the literal code can run:
-  * `np.log(np.linalg.det(K))` underflows to -inf for N >~ 1000
-    (`point_selector.py:118`) -> `nlml(..., stable=True)` uses `slogdet`;
+  * `np.log(np.linalg.det(K))` underflows to -inf once det K < 2^-1074: with the 1e-4
+    jitter from about M = 80-90 points on the reference's own grids, earlier for long
+    length scales (`point_selector.py:118`) -> `nlml(..., stable=True)` uses `slogdet`;
   * the full C x C prior/posterior covariance (`point_selector.py:78,91`) of which
     only the diagonal is used (`:98`) -> `posterior_diag` computes the diagonal
     in chunks.  Like the reference it uses an explicit `np.linalg.inv`.

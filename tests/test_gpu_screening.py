@@ -112,9 +112,9 @@ def test_the_bound_dominates_the_exact_score(eng):
 
 # ------------------------------------------------------------------ grid sweeps: means from GEMMs (csrc/screen_gemm.cu)
 @pytest.mark.parametrize("n,lens,rng_", [
-    (700, (7, 5, 9, 11), (123, 3400)),            # odd number of trailing settings (padded row stride), range cut inside rows
+    (700, (9, 7, 5, 9, 11), (123, 30000)),           # odd number of trailing settings (padded row stride), range cut inside rows
     (1200, (6,) * 6, (0, 6 ** 6)),                # balanced 3 + 3 split, stored operands
-    (300, (3, 50, 40), (777, 5999)),              # long axes: no factor tables, the screen falls back to the mean-only panel pass
+    (300, (13, 50, 40), (777, 25999)),            # long axes: no factor tables, the screen falls back to the mean-only panel pass
     (2100, (4,) * 9, (1000, 260_000)),            # nine axes
 ])
 def test_gemm_screen_returns_the_exact_winner_on_ragged_grids_and_ranges(eng, n, lens, rng_):
@@ -185,4 +185,35 @@ def test_gemm_mean_slack_covers_the_rounding_difference(eng):
     err = np.abs(mu_gemm - mu).max()
     record_error("gemm screen", "max |mu_gemm - mu_exact| / eps", err / eps, 1.0, note=f"eps = {eps:.2e}, |alpha|_1 = {np.abs(alpha).sum():.3g}")
     assert err <= eps
+    fit.close()
+
+
+def test_global_seed_shards_pick_the_full_winner(eng):
+    """bogp_set_global_seed: every shard of a sharded arg-max seeds its screen with the same strided sample of the WHOLE grid.
+    The winner over the shards is the winner of the full sweep (a shard may report a seed candidate outside its range), and
+    shards far from the winner no longer score their plateau exactly."""
+    from bayesian_optimisation_b200.engine import CandidateGrid, JITTER_POSTERIOR
+    from bayesian_optimisation_b200.sharding import reduce_pairs, shard_range
+    X, y, ell = o.synthetic_problem(900, 6, seed=31)
+    X = 0.25 * X                                               # all measurements in one corner: most of the grid is a flat plateau
+    grid = CandidateGrid([np.linspace(0, 1, 8)] * 6)           # 262144 candidates
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    eng.set_screening(False)
+    full = eng.acquire(fit, grid)
+    eng.set_screening(True)
+    tot = {}
+    for glob in (False, True):
+        eng.set_global_seed(glob)
+        eng.screen_stats()
+        pairs = []
+        for r in range(8):
+            b, e = shard_range(grid.size, r, 8)
+            res = eng.acquire(fit, grid, b, e)
+            pairs.append((res.best_score, res.best_index))
+        eng.set_global_seed(False)
+        assert reduce_pairs(pairs) == (full.best_score, full.best_index)
+        tot[glob] = eng.screen_stats()
+    record_error("global seed", "survivors of 8 shards with the global seed / with shard-local seeds", tot[True][1] / max(1, tot[False][1]),
+                 note=f"{tot[True][1]} vs {tot[False][1]} of {grid.size}")
+    assert tot[True][1] < grid.size // 4            # (which of the two seeds leaves fewer survivors depends on the landscape)
     fit.close()

@@ -18,7 +18,7 @@ from bayesian_optimisation_b200.sharding import allreduce_maxloc_device, shard_r
 
 import argparse
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=bench.N_OBS)
+ap.add_argument("--n", "--nobs", dest="n", type=int, default=bench.N_OBS, help="measured points (use --nobs under torchrun, whose own parser claims --n)")
 ap.add_argument("--dim", type=int, default=bench.DIM)
 ap.add_argument("--grid", type=int, default=bench.GRID_PTS, help="grid points per axis")
 ap.add_argument("--kind", default="ei", choices=["ei", "lcb"])
@@ -35,6 +35,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 eng = GPEngine(local)
 eng.set_screening(not args.no_screen)
+eng.set_global_seed(world > 1)          # every shard screens against the same floor
 if (args.n, args.dim) == (bench.N_OBS, bench.DIM):
     X, y, ell = bench.synthetic()
 else:

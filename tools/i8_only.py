@@ -10,7 +10,8 @@ count = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 16384
 eng = GPEngine(0)
 eng.set_acquire_path(sys.argv[5] if len(sys.argv) > 5 else "i8")
-eng.set_screening(False)      # every candidate through the N^2 product (the screen would leave almost nothing to profile)
+eng.set_screening(False)
+eng.set_fused(len(sys.argv) > 6 and sys.argv[6] == "fused")      # one persistent fused kernel per sweep instead of the separate kernels      # every candidate through the N^2 product (the screen would leave almost nothing to profile)
 X, y, ell = o.synthetic_problem(n, d)
 grid = CandidateGrid([np.linspace(0, 1, 10 if d < 10 else 8)] * d)
 fit = eng.fit(X, y, ell, JITTER_POSTERIOR)

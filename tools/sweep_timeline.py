@@ -9,6 +9,7 @@ from bayesian_optimisation_b200.engine import GPEngine, CandidateGrid, JITTER_PO
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 count = int(sys.argv[3]) if len(sys.argv) > 3 else 10 ** 8
+begin = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 eng = GPEngine(0)
 if (n, d) == (bench.N_OBS, bench.DIM):
     X, y, ell = bench.synthetic()
@@ -16,13 +17,14 @@ else:
     from oracle import gp_oracle as o
     X, y, ell = o.synthetic_problem(n, d)
 grid = CandidateGrid([np.linspace(0, 1, 10 if d < 10 else 8)] * d)
-count = min(count, grid.size)
+count = min(count, grid.size - begin)
 fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
 fb = float(y.min())
 eng.acquire(fit, grid, 0, min(count, 1 << 22), kind=ACQ_EI, f_best=fb)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    r = eng.acquire(fit, grid, 0, count, kind=ACQ_EI, f_best=fb)
+    kind = 0 if len(sys.argv) > 5 and sys.argv[5] == "lcb" else ACQ_EI
+    r = eng.acquire(fit, grid, begin, begin + count, kind=kind, f_best=fb)
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "sweep_trace.json")
 prof.export_chrome_trace(path)
