@@ -36,7 +36,8 @@
 namespace bogp {
 
 constexpr int kFusedThreads  = 576;
-constexpr int kFusedMiscOff  = kI8Stages * kI8Stage;          // barriers, tile ring, reduction scratch
+constexpr int kFusedStages   = 4;                                // stages of the operand ring (a power of two)
+constexpr int kFusedMiscOff  = kFusedStages * kI8Stage;          // barriers, tile ring, reduction scratch
 constexpr int kFusedMiscSize = 2560;
 constexpr long long kFusedNoIndex = 0x7fffffffffffffffLL;
 
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) acquire_fused_i8_kernel(cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* misc = smem_raw + kFusedMiscOff;
     uint64_t* full       = reinterpret_cast<uint64_t*>(misc);            // [4]
-    uint64_t* empt       = full + kI8Stages;                              // [4]
-    uint64_t* accbar     = empt + kI8Stages;                              // MMAs of a tile done -> epilogue
+    uint64_t* empt       = full + kFusedStages;                              // [4]
+    uint64_t* accbar     = empt + kFusedStages;                              // MMAs of a tile done -> epilogue
     uint64_t* tmem_empty = accbar + 1;                                    // epilogue has drained TMEM -> next tile's MMAs
     uint64_t* tile_full  = tmem_empty + 1;                                // [4] tile descriptor published
     uint32_t* tmem_slot  = reinterpret_cast<uint32_t*>(tile_full + 4);    // +112
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) acquire_fused_i8_kernel(cons
     const unsigned long long total_items = (unsigned long long)((nct + g.G - 1) / g.G) * (unsigned long long)per_group;
 
     if (tid == 0) {
-        for (int s = 0; s < kI8Stages; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 1); mbar_init(&tile_full[s], 1); }
+        for (int s = 0; s < kFusedStages; s++) { mbar_init(&full[s], 1); mbar_init(&empt[s], 1); mbar_init(&tile_full[s], 1); }
         mbar_init(accbar, 1);
         mbar_init(tmem_empty, 8);
         mbar_init(&psm.bar, 1);
@@ -163,8 +164,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) acquire_fused_i8_kernel(cons
                 const uint8_t* wsrc = g.wq + (int64_t)ib * (ib + 1) / 2 * (kI8BM / kI8KB) * kI8ATile;
                 const uint8_t* psrc = g.pa.panel + (ct % g.R) * (int64_t)(g.pa.n_pad / kI8KB) * kI8BTile;
                 for (int kt = 0; kt < nk; kt++, it++) {
-                    const int s = (int)(it & (kI8Stages - 1));
-                    if (it >= (uint32_t)kI8Stages) mbar_wait(&empt[s], ((it / kI8Stages) - 1) & 1);
+                    const int s = (int)(it & (kFusedStages - 1));
+                    if (it >= (uint32_t)kFusedStages) mbar_wait(&empt[s], ((it / kFusedStages) - 1) & 1);
                     unsigned char* dst = smem_raw + (size_t)s * kI8Stage;
                     mbar_expect_tx(&full[s], kI8Stage);
                     bulk_g2s(dst, wsrc + (int64_t)kt * kI8ATile, kI8ATile, &full[s]);
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) acquire_fused_i8_kernel(cons
                 if (t > 0) mbar_wait(tmem_empty, (uint32_t)(t - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kt = 0; kt < nk; kt++, it++) {
-                    const int s = (int)(it & (kI8Stages - 1));
-                    mbar_wait(&full[s], (it / kI8Stages) & 1);
+                    const int s = (int)(it & (kFusedStages - 1));
+                    mbar_wait(&full[s], (it / kFusedStages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = smem_u32(smem_raw + (size_t)s * kI8Stage);
                     const uint32_t b0 = a0 + kI8ATile;

@@ -346,6 +346,7 @@ def run_gpu_arm(args):
     screened_value = scr_total * args.steps / (scr_ms * 1e-3)
     n_scr, n_surv = eng.screen_stats()
     screened = {"value": screened_value, "unit": UNIT, "candidates_per_step": scr_total, "ms_per_step": scr_ms / args.steps,
+                "mean_gemm_tflops_lower_bound": 2.0 * N_OBS * scr_per_rank / (scr_ms / args.steps * 1e-3) * 1e-12,      # per GPU; the step also holds the fit and the exact passes
                 "survivor_fraction_rank0": (n_surv / n_scr) if n_scr else None,
                 "same_winner_as_full_sweep": bool(scr_last == last),
                 "what": "arg-max-only EI sweep with the posterior-mean screen (include/bogp.h bogp_set_screening), fit included in every step: exact "
@@ -434,7 +435,11 @@ def run_gpu_arm(args):
                     "candidates_per_launch": launch_c, "executed_int8_ops_per_launch": int8_ops, "algorithmic_flops_per_launch": flops,
                     "fp64_equivalent_tflops": fp64_equiv, "frac_of_fp64_pipe_peak": fp64_equiv / f64_burst,
                     "peak_source": "of measured: int8 tcgen05.mma issue-rate peak of THIS GPU (burst, max clocks), measured in this run; "
-                                   "MEASURED_PEAKS.json has no int8 entry", "peaks": peaks, "share_of_sweep": share}
+                                   "MEASURED_PEAKS.json has no int8 entry", "peaks": peaks, "share_of_sweep": share,
+                    "frac_clock_scaled": (achieved / i8_burst) / (clocks["sm_mhz"] / clocks["sm_max_mhz"]) if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None,
+                    "frac_clock_scaled_note": "frac divided by (median SM clock under load / max SM clock): the sweep runs at the 1 kW power cap, "
+                                              "the burst peak was measured at max clocks; ncu (profiles/r02_trigemm_i8_65536_ncu_raw.csv) reads 89 % of the "
+                                              "utcimma int8 peak at its own clock"}
         else:
             roof = {"bound": "tensor", "kernel": "trigemm_kernel (FP64 DMMA)", "achieved": fp64_equiv, "peak": f64_burst, "unit": "TFLOP/s",
                     "frac": fp64_equiv / f64_burst, "traffic": traffic, "traffic_source": tnote, "ms_per_launch": per_launch_ms,

@@ -8,7 +8,7 @@ from bayesian_optimisation_b200.engine import GPEngine, CandidateGrid, JITTER_PO
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 count = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
-groups = [int(g) for g in sys.argv[4].split(",")] if len(sys.argv) > 4 else [500, 900]
+groups = [int(g) for g in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
 eng = GPEngine(0)
 eng.set_screening(False)
 if (n, d) == (bench.N_OBS, bench.DIM):
@@ -35,7 +35,6 @@ def prof(label):
     print(f"   {label}: " + ", ".join(f"{k} {v[0]:.2f} ms / {v[1]}" for k, v in pr.items() if v[1]), flush=True)
 
 eng.set_fused(False); run("separate kernels"); prof("separate, tables")
-eng.set_fused(False, 400); run("separate, no tables"); prof("separate, no tables")
 for g in groups:
     eng.set_fused(True, g); run(f"fused, group={g or 'auto'}")
 eng.set_fused(False); run("separate kernels (again)")
