@@ -968,5 +968,6 @@ const double* fit_xpad(const bogp_fit* f) { return f->x_pad; }
 const double* fit_inv_ell2(const bogp_fit* f) { return f->inv_ell2; }
 const double* fit_alpha(const bogp_fit* f) { return f->alpha; }
 int64_t fit_n(const bogp_fit* f) { return f->n; }
+double fit_jitter(const bogp_fit* f) { return f->jitter; }
 int fit_dim(const bogp_fit* f) { return f->dim; }
 }

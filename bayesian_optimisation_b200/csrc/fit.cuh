@@ -74,6 +74,7 @@ const double* fit_xpad(const bogp_fit* f);
 const double* fit_inv_ell2(const bogp_fit* f);
 const double* fit_alpha(const bogp_fit* f);
 int64_t fit_n(const bogp_fit* f);
+double fit_jitter(const bogp_fit* f);
 int fit_dim(const bogp_fit* f);
 
 }  // namespace bogp

@@ -45,6 +45,109 @@ __global__ void __launch_bounds__(256) gs_prod_kernel(GsGeom g, int ka, int kb, 
     out[(int64_t)blockIdx.x * g.n_pad + j] = v;
 }
 
+// The same product without alpha, rounded to fp32, padding rows zeroed: the B operand of the max-times product below.
+__global__ void __launch_bounds__(256) gs_prod32_kernel(GsGeom g, int ka, int kb, float* __restrict__ out) {
+    const int j = blockIdx.y * 256 + threadIdx.x;
+    long long t = blockIdx.x;
+    int dig[BOGP_MAX_DIM];
+    for (int k = kb - 1; k >= ka; k--) { dig[k] = (int)(t % g.len[k]); t /= g.len[k]; }
+    double v = 1.0;
+    for (int k = ka; k < kb; k++) v *= g.ft[g.toffT[k] + (int64_t)dig[k] * g.n_pad + j];
+    out[(int64_t)blockIdx.x * g.n_pad + j] = j < g.n ? (float)v : 0.0f;
+}
+
+// Nearest-measurement bound of the posterior variance.  For ANY measurement j, sigma^2(c) <= prior - k_j(c)^2 / K_jj (the
+// variance given one measurement bounds the variance given all: k^T K^-1 k >= k_j^2 / K_jj for positive definite K), so with
+// m(c) = max_j k_j(c) the screen may use sigma_ub(c) = sqrt(prior - m^2 / K_jj) instead of sqrt(prior) -- decisive for
+// explore * sigma - mu with a large explore, whose bound is otherwise loose exactly where mu is most negative (near the
+// measurements).  On a grid m[p, t] = max_j G[p, j] F1[t, j] is a MAX-TIMES matrix product; it runs in fp32 on the CUDA
+// cores (64 products and 64 maxima per thread and k; the result only has to be a lower bound of the true maximum, so it
+// is scaled by 1 - 2^-21 afterwards, eight times the three roundings involved).  A[r, k] is generated from one or two
+// stored fp64 product tables (the stored G, or the two composite tables of the generated mode) and rounded to fp32.
+struct GsMaxArgs {
+    const double* tab0; const double* tab1; long long radix1;   // A[r, k] = tab0[d0 * ld + k] (* tab1[d1 * ld + k]); p = d0 * radix1 + d1 (tab1 null: d0 = p)
+    long long ld;
+    const float* F1;                                            // [T][ld]
+    float* out; int ldo;                                        // out[(p - p0) * ldo + t]
+    long long p0; int M, N, K;
+};
+
+constexpr int kMxKB = 16;
+template <bool TWO>      // TWO: A is the product of two table rows (generated mode), else one stored row
+__global__ void __launch_bounds__(256, 2) gs_kmax_kernel(GsMaxArgs a) {
+    __shared__ __align__(16) float sA[2][kMxKB][128];
+    __shared__ __align__(16) float sB[2][kMxKB][128];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    // loader: thread -> (row / column tid / 2, 8 consecutive k)
+    const int lr = tid >> 1, lk = (tid & 1) * 8;
+    const long long p = a.p0 + m0 + lr;
+    const bool rowok = m0 + lr < a.M, colok = n0 + lr < a.N;
+    const double* r0 = a.tab0 + (TWO ? p / a.radix1 : p) * a.ld + lk;
+    const double* r1 = TWO ? a.tab1 + (p % a.radix1) * a.ld + lk : nullptr;
+    const float* rb = a.F1 + (long long)(n0 + lr) * a.ld + lk;
+    double2 pa[4], pb[4]; float4 pf[2];
+    auto fetch = [&](int k0) {
+        if (rowok) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) pa[i] = __ldg(reinterpret_cast<const double2*>(r0 + k0) + i);
+            if (TWO) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) pb[i] = __ldg(reinterpret_cast<const double2*>(r1 + k0) + i);
+            }
+        }
+        if (colok) { pf[0] = __ldg(reinterpret_cast<const float4*>(rb + k0)); pf[1] = __ldg(reinterpret_cast<const float4*>(rb + k0) + 1); }
+    };
+    auto stash = [&](int buf) {
+        float va[8], vb[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double x = rowok ? pa[i].x : 0.0, y = rowok ? pa[i].y : 0.0;
+            if (TWO && rowok) { x *= pb[i].x; y *= pb[i].y; }
+            va[2 * i] = (float)x; va[2 * i + 1] = (float)y;
+        }
+        vb[0] = pf[0].x; vb[1] = pf[0].y; vb[2] = pf[0].z; vb[3] = pf[0].w; vb[4] = pf[1].x; vb[5] = pf[1].y; vb[6] = pf[1].z; vb[7] = pf[1].w;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { sA[buf][lk + i][lr] = va[i]; sB[buf][lk + i][lr] = colok ? vb[i] : 0.0f; }
+    };
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    const int nk = a.K / kMxKB;
+    for (int kt = 0; kt < nk; kt++) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) fetch((kt + 1) * kMxKB);
+#pragma unroll
+        for (int k = 0; k < kMxKB; k++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8]), a1 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 8]), b1 = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaxf(acc[i][j], av[i] * bv[j]);
+        }
+        if (kt + 1 < nk) stash(buf ^ 1);           // the other buffer was last read in iteration kt - 1, before the barrier below
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int row = m0 + ty * 8 + i;
+        if (row >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int col = n0 + tx * 8 + j;
+            if (col < a.N) a.out[(long long)row * a.ldo + col] = acc[i][j];
+        }
+    }
+}
+
 // mu[p - p0, t] = sum_j G[p, j] F[t, j] with G generated on the fly (gemm_f64.cuh, A_GEN): G[p, j] = (((1 f_0) f_1) ... f_kl-1)
 // from the transposed table rows, never stored.  grid (ceil(T / BN), ceil(prefixes / 128)), 256 threads.
 template <int BN>
@@ -97,6 +200,7 @@ struct GsScreenArgs {
     const double* mu; long long base; int ldc; long long ttot;    // mu[(c - base) / T * ldc + (c - base) % T]
     long long lo, hi;                                             // candidates of this chunk inside the requested range
     const double* alpha_l1; double eps_factor;
+    const float* kmax; int ldk; double prior, kjj_inv;           // nearest-measurement variance bound (or null)
     int kind; double explore, f_best, sigma_max;
     const bogp_result* best;
     long long* surv_idx; int* count;
@@ -111,7 +215,13 @@ __global__ void __launch_bounds__(256) gs_screen_kernel(GsScreenArgs a) {
         const long long r = c - a.base;
         const long long pl = r / a.ttot;
         const double mu = a.mu[pl * a.ldc + (r - pl * a.ttot)] - a.eps_factor * a.alpha_l1[0];      // rigorous lower bound of the exact mean
-        double bound = acquisition_value(a.kind, mu, a.sigma_max, a.explore, a.f_best);
+        double smax = a.sigma_max;
+        if (a.kmax) {      // sigma^2 <= prior - m^2 / K_jj, m a lower bound of max_j k_j; 1e-8 covers the rounding of the computed sigma^2 (~1e-13)
+            const double m = (double)a.kmax[pl * a.ldk + (r - pl * a.ttot)] * (1.0 - 4.76837158203125e-07);
+            const double s = sqrt(a.prior - m * m * a.kjj_inv + 1e-8);
+            smax = s < smax ? s : smax;
+        }
+        double bound = acquisition_value(a.kind, mu, smax, a.explore, a.f_best);
         if (a.kind == BOGP_ACQ_EI) bound += 1e-12 * (fabs(a.f_best - mu) + a.sigma_max);
         keep = !(bound < a.best->score);                          // NaN means and bounds are kept: the exact kernels decide
     }
@@ -203,9 +313,18 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         gen.tab = comp; gen.kl = 2; gen.toff[0] = 0; gen.toff[1] = (int)((size_t)P1 * n_pad);
         gg.kl = 2; gg.len[0] = (int)P1; gg.len[1] = (int)P2;
     }
+    // nearest-measurement variance bound (gs_kmax_kernel): for explore * sigma - mu, whose sigma <= sigma_max bound is loose
+    // near the measurements; EI screens well without it (6e-5 of the 10^8 grid survive) and skips the extra pass
+    GsMaxArgs mx{};
+    const bool stored_ok = stored, comp_ok = ka > 0, axis_ok = !stored && ka == 0 && kl == 1;
+    bool want_kmax = kind == BOGP_ACQ_LCB && explore > 0.0 && (stored_ok || comp_ok || axis_ok);
+    size_t f1_bytes = want_kmax ? ((size_t)T * n_pad * 4 + 255) / 256 * 256 : 0;
+    if (want_kmax && f1_bytes + comp_bytes + ((size_t)8 << 20) > rest_bytes) { want_kmax = false; f1_bytes = 0; }
+    const int ldo = (int)((T + 3) / 4 * 4);
     // rows (settings of the leading axes) per chunk: at least ~2.5 M candidates, and a number of 128-row tiles that fills
     // whole waves of the SMs (the smallest row count with >= 88 % of the last wave used, else the best one that fits)
-    const size_t per_row = (size_t)ldc * 8 + (size_t)kGsBatch * T * 8;
+    const size_t per_row = (size_t)ldc * 8 + (size_t)kGsBatch * T * 8 + (want_kmax ? (size_t)ldo * 4 : 0);
+    comp_bytes += f1_bytes;                                        // (the fp32 operand sits right behind the composite tables)
     const long long col_tiles = (T + (T <= 64 ? 63 : 127)) / (T <= 64 ? 64 : 128);
     long long Pc = 128; double beste = 0.0;
     for (long long r = 1; r <= 1024; r++) {
@@ -216,9 +335,11 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         if (e >= 0.88 && r * 128 * T >= 2500000) { Pc = r * 128; break; }
     }
     if ((size_t)Pc * per_row > rest_bytes - comp_bytes) return 1;
+    float* F1 = reinterpret_cast<float*>(rest + comp_bytes - f1_bytes);
     double* mu = reinterpret_cast<double*>(rest + comp_bytes);
     long long* surv = reinterpret_cast<long long*>(mu + (size_t)Pc * ldc);
-    int* count = reinterpret_cast<int*>(surv + (size_t)kGsBatch * Pc * T);
+    float* kmx = reinterpret_cast<float*>(surv + (size_t)kGsBatch * Pc * T);
+    int* count = reinterpret_cast<int*>(kmx + (want_kmax ? (size_t)Pc * ldo : 0));
     const long long cap = kGsBatch * Pc * T;                       // survivors of a batch of chunks: at most all of their candidates
     if (cap < kGsSeed) return 1;
 
@@ -230,6 +351,12 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
     if (ka > 0) {
         gs_prod_kernel<<<dim3((unsigned)P1, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, 0, ka, nullptr, comp); BOGP_LAUNCH_CHECK(ctx);
         gs_prod_kernel<<<dim3((unsigned)P2, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, ka, kl, nullptr, comp + (size_t)P1 * n_pad); BOGP_LAUNCH_CHECK(ctx);
+    }
+    if (want_kmax) {
+        gs_prod32_kernel<<<dim3((unsigned)T, (unsigned)(n_pad / 256)), 256, 0, st>>>(g, kl, g.dim, F1); BOGP_LAUNCH_CHECK(ctx);
+        mx.tab0 = stored_ok ? Gs : (comp_ok ? comp : g.ft + g.toffT[0]);
+        mx.tab1 = comp_ok && !stored_ok ? comp + (size_t)P1 * n_pad : nullptr; mx.radix1 = P2 > 0 ? P2 : 1;
+        mx.ld = n_pad; mx.F1 = F1; mx.out = kmx; mx.ldo = ldo; mx.N = (int)T; mx.K = (int)n_pad;
     }
 
     // exact scoring of the candidates listed in surv[0 .. *count): one launch of the fused persistent kernel
@@ -261,6 +388,7 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
     sa.eps_factor = (2.0 * (double)n_pad + 16.0) * 1.1102230246251565e-16 * 1.0002;
     sa.kind = kind; sa.explore = explore; sa.f_best = f_best; sa.sigma_max = sqrt(prior_diag);
     sa.best = d_result; sa.surv_idx = surv; sa.count = count;
+    sa.kmax = want_kmax ? kmx : nullptr; sa.ldk = ldo; sa.prior = prior_diag; sa.kjj_inv = 1.0 / (1.0 + fit_jitter(fit));
     sa.stats = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 16);
     const long long p_begin = c_begin / T, p_end = (c_end + T - 1) / T;
     int pending = 0;                                               // whole chunks screened since the last exact pass
@@ -275,6 +403,12 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         else if (T <= 64) rc = launch_mu_gemm<64>(ctx, m, gen, gg, p0);
         else              rc = launch_mu_gemm<128>(ctx, m, gen, gg, p0);
         if (rc) return rc;
+        if (want_kmax) {
+            mx.p0 = p0; mx.M = (int)pc;
+            const dim3 mgrid((unsigned)((T + 127) / 128), (unsigned)((pc + 127) / 128));
+            if (mx.tab1) gs_kmax_kernel<true><<<mgrid, 256, 0, st>>>(mx); else gs_kmax_kernel<false><<<mgrid, 256, 0, st>>>(mx);
+            BOGP_LAUNCH_CHECK(ctx);
+        }
         sa.base = p0 * T;
         // The chunk's candidates are screened in row ranges, each followed by the exact scoring of its survivors.  The running
         // best rises fastest at the beginning, so the ranges start small (~250 k candidates) and double after every exact pass

@@ -326,10 +326,10 @@ def run_gpu_arm(args):
     scr_per_rank = min(1 << 26, grid.size // world)
     scr_total = scr_per_rank * world
 
-    def screened_step(k):
+    def screened_step(k, kind=ACQ_EI):
         fit = eng.fit(dX, dy, ell, JITTER_POSTERIOR)
         b0 = (k * scr_total) % max(1, grid.size - scr_total + 1) + rank * scr_per_rank
-        res = eng.acquire(fit, grid, b0, b0 + scr_per_rank, kind=ACQ_EI, f_best=f_best, chunk=args.chunk, sync=False)
+        res = eng.acquire(fit, grid, b0, b0 + scr_per_rank, kind=kind, explore=4.0, f_best=f_best, chunk=args.chunk, sync=False)
         out = allreduce_maxloc_device(eng, res.record)
         fit.close()
         return out
@@ -352,6 +352,17 @@ def run_gpu_arm(args):
                 "what": "arg-max-only EI sweep with the posterior-mean screen (include/bogp.h bogp_set_screening), fit included in every step: exact "
                         "(score, index); the means of all grid candidates come from fp64 GEMMs over per-axis kernel-factor tables "
                         "(csrc/screen_gemm.cu), the N^2 product runs only for candidates whose bound A(mu - eps, sqrt(prior)) reaches the running best"}
+    # the reference's own acquisition (explore * sigma - mu, explore = 4): its screen also needs the nearest-measurement variance
+    # bound (a max-times product on the CUDA cores, csrc/screen_gemm.cu gs_kmax_kernel), so a step is about twice as long
+    screened_step(0, kind=0)
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for k in range(args.steps):
+        screened_step(k, kind=0)
+    q1.record()
+    barrier()
+    screened["lcb_value"] = scr_total * args.steps / (max_over_ranks(q0.elapsed_time(q1)) * 1e-3)
     eng.set_screening(False)
 
     # ---- end to end through the reference-facing class: pageable host numpy in, host numpy out.  Under torchrun every

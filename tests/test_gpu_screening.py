@@ -217,3 +217,31 @@ def test_global_seed_shards_pick_the_full_winner(eng):
                  note=f"{tot[True][1]} vs {tot[False][1]} of {grid.size}")
     assert tot[True][1] < grid.size // 4            # (which of the two seeds leaves fewer survivors depends on the landscape)
     fit.close()
+
+
+def test_nearest_measurement_variance_bound_dominates_sigma(eng):
+    """gs_kmax_kernel: sigma^2(c) <= prior - max_j k_j(c)^2 / K_jj for the device's own sigma, with the fp32 max-times
+    arithmetic restated on the host (products of fp32-rounded factors, scaled by 1 - 2^-21) -- and how much tighter than
+    sqrt(prior) it is for the candidates that matter."""
+    from bayesian_optimisation_b200.engine import CandidateGrid, JITTER_POSTERIOR, PRIOR_DIAG
+    n, d, G = 1100, 6, 7
+    X, y, ell = o.synthetic_problem(n, d, seed=17)
+    axes = [np.linspace(0, 1, G)] * d
+    fit = eng.fit(X, y, ell, JITTER_POSTERIOR)
+    res = eng.acquire(fit, CandidateGrid(axes), outputs=True)
+    sig = res.sigma.cpu().numpy()
+    P = o.candidate_grid(axes)
+    K = o.kernel_rbf_chunked(X, P, ell)                            # (n, C)
+    m = (K.astype(np.float32).max(axis=0).astype(np.float64)) * (1.0 - 2.0 ** -21) * (1.0 - 2.0 ** -22)      # looser than the kernel's value
+    s_ub = np.sqrt(PRIOR_DIAG - m * m / (1.0 + JITTER_POSTERIOR) + 1e-8)
+    assert np.all(sig <= s_ub)
+    record_error("kmax bound", "mean sigma_ub / sigma_max (mean sigma / sigma_max)", float(s_ub.mean() / np.sqrt(PRIOR_DIAG)),
+                 note=f"{sig.mean() / np.sqrt(PRIOR_DIAG):.3f}")
+    # screened LCB sweep with the bound == unscreened, and far fewer survivors than with sigma_max alone
+    full, scr, screened, survived = _both(eng, fit, CandidateGrid(axes), 0, len(P))
+    assert (scr.best_score, scr.best_index) == (full.best_score, full.best_index)
+    lcb = res.acq.cpu().numpy()
+    loose = int((4.0 * np.sqrt(PRIOR_DIAG) - res.mu.cpu().numpy() >= lcb.max()).sum())
+    record_error("kmax bound", "survivors with the bound / survivors a sigma_max screen against the FINAL best would leave", survived / max(1, loose),
+                 note=f"{survived} vs {loose} of {len(P)}")
+    fit.close()
