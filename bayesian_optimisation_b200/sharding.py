@@ -115,21 +115,15 @@ def all_gather_slices(parts: Sequence[np.ndarray], c_total: int, rank: int, worl
     per = -(-c_total // world)
     k = len(parts)
     dev = _collective_device(group)
-    mine = torch.zeros(k * per, dtype=torch.float64, device=dev)      # padded to the common slice size; one H2D copy per array
+    mine = torch.zeros((k, per), dtype=torch.float64)
     for j, p in enumerate(parts):
-        p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1)
-        mine[j * per:j * per + len(p)].copy_(torch.from_numpy(p))
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        mine[j, :len(p)] = torch.from_numpy(p)
+    mine = mine.reshape(-1).to(dev)
     out = torch.empty(world * k * per, dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, mine, group=group)
-    # (rank, array, slice) -> (array, rank, slice) on the device, then ONE copy per array straight into the array the caller
-    # keeps (no intermediate host tensor, no second host copy)
-    full = out.reshape(world, k, per).permute(1, 0, 2).reshape(k, world * per)
-    res = []
-    for j in range(k):
-        dst = np.empty(c_total, dtype=np.float64)
-        torch.from_numpy(dst).copy_(full[j, :c_total])
-        res.append(dst)
-    return res
+    full = out.reshape(world, k, per).permute(1, 0, 2).reshape(k, world * per)[:, :c_total].cpu().numpy()
+    return [np.ascontiguousarray(full[j]) for j in range(k)]
 
 
 def all_gather_strided(part: np.ndarray, r_total: int, rank: int, world: int, group=None) -> np.ndarray:
