@@ -399,7 +399,10 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         GemmArgs m{};
         m.A = stored ? Gs + (size_t)p0 * n_pad : nullptr; m.lda = n_pad; m.B = Fs; m.ldb = n_pad; m.C = mu; m.ldc = ldc;
         m.M = (int)pc; m.N = (int)T; m.K = (int)n_pad; m.alpha = 1.0; m.accumulate = 0; m.lower_only = 0;
-        if (stored)       rc = (T <= 64) ? launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, m, 1) : launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, m, 1);
+        if (stored) {     // TMA-fed persistent NT kernel with dynamic tile scheduling (gemm_tma.cu), else the cp.async kernel
+            rc = launch_gemm_tma_nt(ctx, m);
+            if (rc == 1) rc = (T <= 64) ? launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, m, 1) : launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, m, 1);
+        }
         else if (T <= 64) rc = launch_mu_gemm<64>(ctx, m, gen, gg, p0);
         else              rc = launch_mu_gemm<128>(ctx, m, gen, gg, p0);
         if (rc) return rc;
