@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "fit.cuh"
 #include "gemm_f64.cuh"
+#include <cuda_fp16.h>
 
 namespace bogp {
 
@@ -73,10 +74,14 @@ struct GsMaxArgs {
 };
 
 constexpr int kMxKB = 16;
+// Packed-half arithmetic: two (product, maximum) pairs per instruction pair (HMUL2 + HMNMX2).  The operands are rounded
+// to fp16 (a duplicated into both halves, two consecutive columns of B per word), three roundings of 2^-11 each in the
+// normal range and of at most 2^-25 absolute below it, so the screen uses max(0, m (1 - 2^-9) - 2^-22) as its lower bound of
+// the true maximum (GsScreenArgs.kmax_scale / kmax_sub): 0.2 % looser than fp32, far below what the bound gains.
 template <bool TWO>      // TWO: A is the product of two table rows (generated mode), else one stored row
 __global__ void __launch_bounds__(256, 2) gs_kmax_kernel(GsMaxArgs a) {
-    __shared__ __align__(16) float sA[2][kMxKB][128];
-    __shared__ __align__(16) float sB[2][kMxKB][128];
+    __shared__ __align__(16) __half2 sA[2][kMxKB][128];       // (a, a)
+    __shared__ __align__(16) __half2 sB[2][kMxKB][64];        // (b_2c, b_2c+1)
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
     // loader: thread -> (row / column tid / 2, 8 consecutive k)
@@ -107,14 +112,18 @@ __global__ void __launch_bounds__(256, 2) gs_kmax_kernel(GsMaxArgs a) {
             va[2 * i] = (float)x; va[2 * i + 1] = (float)y;
         }
         vb[0] = pf[0].x; vb[1] = pf[0].y; vb[2] = pf[0].z; vb[3] = pf[0].w; vb[4] = pf[1].x; vb[5] = pf[1].y; vb[6] = pf[1].z; vb[7] = pf[1].w;
+        __half* sBh = reinterpret_cast<__half*>(&sB[buf][0][0]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { sA[buf][lk + i][lr] = va[i]; sB[buf][lk + i][lr] = colok ? vb[i] : 0.0f; }
+        for (int i = 0; i < 8; i++) {
+            sA[buf][lk + i][lr] = __float2half2_rn(va[i]);
+            sBh[(lk + i) * 128 + lr] = __float2half_rn(colok ? vb[i] : 0.0f);
+        }
     };
-    float acc[8][8];
+    __half2 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+        for (int j = 0; j < 4; j++) acc[i][j] = __float2half2_rn(0.0f);
     fetch(0);
     stash(0);
     __syncthreads();
@@ -124,14 +133,15 @@ __global__ void __launch_bounds__(256, 2) gs_kmax_kernel(GsMaxArgs a) {
         if (kt + 1 < nk) fetch((kt + 1) * kMxKB);
 #pragma unroll
         for (int k = 0; k < kMxKB; k++) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8]), a1 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8 + 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 8]), b1 = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 8 + 4]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const uint4 a0 = *reinterpret_cast<const uint4*>(&sA[buf][k][ty * 8]), a1 = *reinterpret_cast<const uint4*>(&sA[buf][k][ty * 8 + 4]);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(&sB[buf][k][tx * 4]);
+            const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const uint32_t bw[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[i][j] = fmaxf(acc[i][j], av[i] * bv[j]);
+                for (int j = 0; j < 4; j++)
+                    acc[i][j] = __hmax2(acc[i][j], __hmul2(*reinterpret_cast<const __half2*>(&aw[i]), *reinterpret_cast<const __half2*>(&bw[j])));
         }
         if (kt + 1 < nk) stash(buf ^ 1);           // the other buffer was last read in iteration kt - 1, before the barrier below
         __syncthreads();
@@ -141,11 +151,22 @@ __global__ void __launch_bounds__(256, 2) gs_kmax_kernel(GsMaxArgs a) {
         const int row = m0 + ty * 8 + i;
         if (row >= a.M) continue;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int col = n0 + tx * 8 + j;
-            if (col < a.N) a.out[(long long)row * a.ldo + col] = acc[i][j];
+        for (int j = 0; j < 4; j++) {
+            const int col = n0 + tx * 8 + 2 * j;
+            const float2 v = __half22float2(acc[i][j]);
+            if (col < a.N) a.out[(long long)row * a.ldo + col] = v.x;
+            if (col + 1 < a.N) a.out[(long long)row * a.ldo + col + 1] = v.y;
         }
     }
+}
+
+// Generated mode with room for a chunk of G: G[p - p0, j] = C1[p / P2, j] * C2[p % P2, j] written out (rows over j), so that the
+// mean GEMM can run in the TMA-fed kernel on stored operands.  grid (rows of the chunk, n_pad / 256)
+__global__ void __launch_bounds__(256) gs_compose_kernel(const double* __restrict__ c1, const double* __restrict__ c2, long long P2, long long p0,
+                                                         int64_t ld, double* __restrict__ G) {
+    const int j = blockIdx.y * 256 + threadIdx.x;
+    const long long p = p0 + blockIdx.x;
+    G[(int64_t)blockIdx.x * ld + j] = c1[(p / P2) * ld + j] * c2[(p % P2) * ld + j];
 }
 
 // mu[p - p0, t] = sum_j G[p, j] F[t, j] with G generated on the fly (gemm_f64.cuh, A_GEN): G[p, j] = (((1 f_0) f_1) ... f_kl-1)
@@ -217,7 +238,8 @@ __global__ void __launch_bounds__(256) gs_screen_kernel(GsScreenArgs a) {
         const double mu = a.mu[pl * a.ldc + (r - pl * a.ttot)] - a.eps_factor * a.alpha_l1[0];      // rigorous lower bound of the exact mean
         double smax = a.sigma_max;
         if (a.kmax) {      // sigma^2 <= prior - m^2 / K_jj, m a lower bound of max_j k_j; 1e-8 covers the rounding of the computed sigma^2 (~1e-13)
-            const double m = (double)a.kmax[pl * a.ldk + (r - pl * a.ttot)] * (1.0 - 4.76837158203125e-07);
+            double m = (double)a.kmax[pl * a.ldk + (r - pl * a.ttot)] * (1.0 - 0.001953125) - 2.384185791015625e-07;     // fp16 max-times: (1 - 2^-9) m - 2^-22
+            m = m > 0.0 ? m : 0.0;
             const double s = sqrt(a.prior - m * m * a.kjj_inv + 1e-8);
             smax = s < smax ? s : smax;
         }
@@ -323,7 +345,9 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
     const int ldo = (int)((T + 3) / 4 * 4);
     // rows (settings of the leading axes) per chunk: at least ~2.5 M candidates, and a number of 128-row tiles that fills
     // whole waves of the SMs (the smallest row count with >= 88 % of the last wave used, else the best one that fits)
-    const size_t per_row = (size_t)ldc * 8 + (size_t)kGsBatch * T * 8 + (want_kmax ? (size_t)ldo * 4 : 0);
+    // generated mode with composite tables: a chunk of G is written out for the TMA-fed GEMM if rows of 8 n_pad bytes fit
+    const bool compose = !stored && ka > 0 && rest_bytes - comp_bytes - f1_bytes > ((size_t)1024 * n_pad * 8 + ((size_t)256 << 20));
+    const size_t per_row = (size_t)ldc * 8 + (size_t)kGsBatch * T * 8 + (want_kmax ? (size_t)ldo * 4 : 0) + (compose ? (size_t)n_pad * 8 : 0);
     comp_bytes += f1_bytes;                                        // (the fp32 operand sits right behind the composite tables)
     const long long col_tiles = (T + (T <= 64 ? 63 : 127)) / (T <= 64 ? 64 : 128);
     long long Pc = 128; double beste = 0.0;
@@ -333,13 +357,15 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         const double e = (double)tiles / (double)(waves * ctx->sm_count);
         if (e > beste + 1e-9) { beste = e; Pc = r * 128; }
         if (e >= 0.88 && r * 128 * T >= 2500000) { Pc = r * 128; break; }
+        if (compose && (r + 1) * 128 * (size_t)n_pad * 8 > ((size_t)512 << 20)) { if (r * 128 * T >= 1000000) { Pc = r * 128; break; } }   // keep the G chunk under 512 MB (the TMA kernel schedules tiles dynamically)
     }
     if ((size_t)Pc * per_row > rest_bytes - comp_bytes) return 1;
     float* F1 = reinterpret_cast<float*>(rest + comp_bytes - f1_bytes);
     double* mu = reinterpret_cast<double*>(rest + comp_bytes);
     long long* surv = reinterpret_cast<long long*>(mu + (size_t)Pc * ldc);
     float* kmx = reinterpret_cast<float*>(surv + (size_t)kGsBatch * Pc * T);
-    int* count = reinterpret_cast<int*>(kmx + (want_kmax ? (size_t)Pc * ldo : 0));
+    double* Gc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(kmx + (want_kmax ? (size_t)Pc * ldo : 0)) + 255) / 256 * 256);
+    int* count = reinterpret_cast<int*>(Gc + (compose ? (size_t)Pc * n_pad : 0));
     const long long cap = kGsBatch * Pc * T;                       // survivors of a batch of chunks: at most all of their candidates
     if (cap < kGsSeed) return 1;
 
@@ -399,7 +425,15 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         GemmArgs m{};
         m.A = stored ? Gs + (size_t)p0 * n_pad : nullptr; m.lda = n_pad; m.B = Fs; m.ldb = n_pad; m.C = mu; m.ldc = ldc;
         m.M = (int)pc; m.N = (int)T; m.K = (int)n_pad; m.alpha = 1.0; m.accumulate = 0; m.lower_only = 0;
-        if (stored) {     // TMA-fed persistent NT kernel with dynamic tile scheduling (gemm_tma.cu), else the cp.async kernel
+        bool done = false;
+        if (compose) {    // write the chunk of G out, then the TMA-fed kernel on stored operands
+            gs_compose_kernel<<<dim3((unsigned)pc, (unsigned)(n_pad / 256)), 256, 0, st>>>(comp, comp + (size_t)P1 * n_pad, P2, p0, n_pad, Gc); BOGP_LAUNCH_CHECK(ctx);
+            m.A = Gc;
+            rc = launch_gemm_tma_nt(ctx, m);
+            if (rc == 1) m.A = nullptr; else done = true;
+        }
+        if (done) {
+        } else if (stored) {     // TMA-fed persistent NT kernel with dynamic tile scheduling (gemm_tma.cu), else the cp.async kernel
             rc = launch_gemm_tma_nt(ctx, m);
             if (rc == 1) rc = (T <= 64) ? launch_gemm<128, 64, A_MK, B_NK, K_ALL>(ctx, m, 1) : launch_gemm<128, 128, A_MK, B_NK, K_ALL>(ctx, m, 1);
         }
@@ -407,9 +441,11 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
         else              rc = launch_mu_gemm<128>(ctx, m, gen, gg, p0);
         if (rc) return rc;
         if (want_kmax) {
-            mx.p0 = p0; mx.M = (int)pc;
+            GsMaxArgs mq = mx;
+            mq.p0 = p0; mq.M = (int)pc;
+            if (compose && m.A == Gc) { mq.tab0 = Gc; mq.tab1 = nullptr; mq.p0 = 0; }      // the chunk of G that was just written out: one stored row per A row
             const dim3 mgrid((unsigned)((T + 127) / 128), (unsigned)((pc + 127) / 128));
-            if (mx.tab1) gs_kmax_kernel<true><<<mgrid, 256, 0, st>>>(mx); else gs_kmax_kernel<false><<<mgrid, 256, 0, st>>>(mx);
+            if (mq.tab1) gs_kmax_kernel<true><<<mgrid, 256, 0, st>>>(mq); else gs_kmax_kernel<false><<<mgrid, 256, 0, st>>>(mq);
             BOGP_LAUNCH_CHECK(ctx);
         }
         sa.base = p0 * T;

@@ -220,9 +220,9 @@ def test_global_seed_shards_pick_the_full_winner(eng):
 
 
 def test_nearest_measurement_variance_bound_dominates_sigma(eng):
-    """gs_kmax_kernel: sigma^2(c) <= prior - max_j k_j(c)^2 / K_jj for the device's own sigma, with the fp32 max-times
-    arithmetic restated on the host (products of fp32-rounded factors, scaled by 1 - 2^-21) -- and how much tighter than
-    sqrt(prior) it is for the candidates that matter."""
+    """gs_kmax_kernel: sigma^2(c) <= prior - max_j k_j(c)^2 / K_jj for the device's own sigma, with the packed-half max-times
+    arithmetic restated on the host (fp16-rounded values, (1 - 2^-9) m - 2^-22 as the lower bound of the maximum) -- and how
+    much tighter than sqrt(prior) it is for the candidates that matter."""
     from bayesian_optimisation_b200.engine import CandidateGrid, JITTER_POSTERIOR, PRIOR_DIAG
     n, d, G = 1100, 6, 7
     X, y, ell = o.synthetic_problem(n, d, seed=17)
@@ -232,7 +232,7 @@ def test_nearest_measurement_variance_bound_dominates_sigma(eng):
     sig = res.sigma.cpu().numpy()
     P = o.candidate_grid(axes)
     K = o.kernel_rbf_chunked(X, P, ell)                            # (n, C)
-    m = (K.astype(np.float32).max(axis=0).astype(np.float64)) * (1.0 - 2.0 ** -21) * (1.0 - 2.0 ** -22)      # looser than the kernel's value
+    m = np.maximum(0.0, K.astype(np.float16).max(axis=0).astype(np.float64) * (1.0 - 2.0 ** -9) - 2.0 ** -22)
     s_ub = np.sqrt(PRIOR_DIAG - m * m / (1.0 + JITTER_POSTERIOR) + 1e-8)
     assert np.all(sig <= s_ub)
     record_error("kmax bound", "mean sigma_ub / sigma_max (mean sigma / sigma_max)", float(s_ub.mean() / np.sqrt(PRIOR_DIAG)),
