@@ -455,6 +455,7 @@ static int acquire_enqueue(bogp_ctx* ctx, const bogp_fit* fit, const bogp_candid
         (kind != BOGP_ACQ_LCB && kind != BOGP_ACQ_EI)) {
         set_error("bogp_acquire: bad argument"); return BOGP_ERR_BAD_ARG;
     }
+    NvtxRange nvtx("bogp acquisition sweep");
     const int dim = fit_dim(fit);
     const int64_t n_pad = bogp_fit_n_pad(fit);
     const int nI = (int)(n_pad / kAcqBM);

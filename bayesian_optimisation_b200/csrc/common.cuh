@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdarg>
 
+#include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
+
 #include "../../include/bogp.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -22,6 +24,13 @@ constexpr int kAcqKB    = 16;    // k extent of one pipeline stage
 constexpr int kAcqStages = 5;
 
 void set_error(const char* fmt, ...);
+
+// NVTX range around the host side of a library call (what enqueues a fit, a sweep, a batched LML): visible in nsys / ncu
+// timelines next to the kernels it launched.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // Function attributes (opt-in shared memory) are per device: `flags` is a per-kernel static array.
 struct DeviceOnce {

@@ -879,6 +879,7 @@ static int fit_enqueue(bogp_ctx* ctx, const double* d_x, const double* d_y, int6
     if (!ctx || !d_x || !d_y || !d_ell || !d_workspace || !out || n <= 0 || dim <= 0 || dim > BOGP_MAX_DIM) {
         set_error("bogp_fit_create: bad argument"); return BOGP_ERR_BAD_ARG;
     }
+    NvtxRange nvtx("bogp fit: Gram + Cholesky + L^-1 + alpha + nlml");
     const FitLayout l = fit_layout(n, dim);
     if (workspace_bytes < l.total) { set_error("bogp_fit_create: workspace %zu < %zu bytes", workspace_bytes, l.total); return BOGP_ERR_WORKSPACE; }
     if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) != 0) { set_error("bogp_fit_create: workspace must be 256-byte aligned"); return BOGP_ERR_BAD_ARG; }

@@ -279,6 +279,7 @@ extern "C" int bogp_nlml_batched(bogp_ctx* ctx, const double* d_x, const double*
     if (!ctx || !d_x || !d_y || !d_ell || !d_nlml_out || !d_workspace || n <= 0 || dim <= 0 || dim > BOGP_MAX_DIM || r <= 0) {
         set_error("bogp_nlml_batched: bad argument"); return BOGP_ERR_BAD_ARG;
     }
+    NvtxRange nvtx("bogp batched nlml (+ gradient)");
     const LmlLayout l = lml_layout(n, dim, r, d_grad_out != nullptr);
     if (workspace_bytes < l.total) { set_error("bogp_nlml_batched: workspace %zu < %zu bytes", workspace_bytes, l.total); return BOGP_ERR_WORKSPACE; }
     char* base = static_cast<char*>(d_workspace);

@@ -273,6 +273,7 @@ int gemm_screen_sweep(bogp_ctx* ctx, const bogp_fit* fit, const AcqChunk& tab, i
                       double f_best, double prior_diag, void* d_workspace, size_t workspace_bytes, bogp_result* d_result) {
     GsGeom g{};
     if (!gs_geometry(tab, g)) return 1;
+    NvtxRange nvtx("bogp screened grid sweep: mean GEMM + bound + exact survivors");
     const int64_t n_pad = tab.n_pad;
     // workspace: [ring of the fused exact pass][stored operands G, F (stored mode)][mu chunk][survivor indices of a batch of chunks][count]
     const size_t ring = (fused_workspace_bytes(n_pad) + 255) / 256 * 256;
