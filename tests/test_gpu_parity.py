@@ -636,3 +636,42 @@ def test_kernels_stay_inside_their_declared_workspaces(eng, n, d):
         assert intact(lws, lnb), f"nlml_batched (R={R}) wrote past its workspace"
         if ref is not None:
             assert abs(out[0].item() - ref) <= RTOL * abs(ref)
+
+
+@pytest.mark.parametrize("n,lens,chunk", [(300, (6, 5, 7, 9, 8), 512), (1100, (6,) * 7, 2048), (700, (9, 8), 64), (520, (4,) * 9, 4096)])
+def test_round2_sweep_paths_stay_inside_their_declared_workspace(eng, n, lens, chunk):
+    """The same guard-region check for the paths added in round 2, each with exactly `bogp_acquire_workspace_bytes(fit, chunk)`
+    bytes: grid sweeps with per-axis factor tables (separate kernels and the fused persistent kernel with its ring), and
+    screened arg-max-only grid sweeps (mean GEMM in stored or generated mode, max-times bound, survivor lists, exact passes)."""
+    import ctypes as C
+    import torch
+    from bayesian_optimisation_b200 import _lib
+    from bayesian_optimisation_b200.engine import Candidates
+    if eng.acquire_path != "i8":
+        pytest.skip("the round-2 sweep paths belong to the INT8 tensor path")
+    e = _consts()
+    GUARD = 1 << 16
+    d = len(lens)
+    X, y, ell = o.synthetic_problem(n, d, seed=n)
+    fit = eng.fit(X, y, ell, e.JITTER_POSTERIOR)
+    axes = eng.to_device(np.concatenate([np.linspace(0, 1, L) for L in lens]))
+    alen = (C.c_int32 * d)(*lens)
+    total = int(np.prod(lens))
+    cd = Candidates(); cd.d_points, cd.d_axes, cd.h_axis_len, cd.c_total, cd.cross_jitter = None, axes.data_ptr(), alen, total, 0.0
+    nb = (eng.lib.bogp_acquire_workspace_bytes(fit._h, chunk) + 255) // 256 * 256
+    eng._sync_stream()
+    results = []
+    try:
+        for fused, screening, kind in ((False, False, 0), (True, False, 0), (False, True, 0), (False, True, 1)):
+            eng.set_fused(fused); eng.set_screening(screening)
+            ws = torch.full((nb + GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+            bs, bi = C.c_double(), C.c_int64()
+            _lib.check(eng.lib.bogp_acquire(eng._ctx, fit._h, C.byref(cd), 0, total, kind, 4.0, float(y.min()), e.PRIOR_DIAG, None, None, None,
+                                            ws.data_ptr(), nb, C.byref(bs), C.byref(bi)))
+            torch.cuda.synchronize()
+            assert bool((ws[nb:] == 0xA5).all().item()), f"sweep (fused={fused}, screening={screening}, kind={kind}) wrote past its workspace"
+            results.append((kind, bs.value, bi.value))
+    finally:
+        eng.set_fused(False); eng.set_screening(True)
+    assert results[0] == results[1] == results[2]              # separate == fused == screened, bitwise
+    fit.close()
