@@ -344,6 +344,7 @@ int launch_trigemm_i8(bogp_ctx* ctx, const AcqChunk& a, cudaStream_t stream) {
     const bool ub = a.n_pad <= 8192;
     const int nI = a.n_pad / kI8BM;
     int group = (int)((32u << 20) / ((size_t)(a.n_pad / kI8KB) * kI8BTile));     // ~32 MB of panel per group
+    if (ctx->fused_group > 0) group = ctx->fused_group;          // bogp_set_fused(ctx, enable, group): the work-group size of either variant
     group = group < 1 ? 1 : (group > 64 ? 64 : group);
     const int ngroups = (nct + group - 1) / group;
     TriI8Args ta{a.wq, (const uint8_t*)a.panel, a.wscale, a.qpart, nI, nct, a.n_pad, a.S, ub ? 0 : 1, group, a.d_count, a.c0};

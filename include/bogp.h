@@ -77,7 +77,8 @@ int bogp_get_screening(const bogp_ctx* ctx);
  * traffic to HBM, a 60 MB workspace instead of 2 GB) -- or (enable = 0, the default: measured ~6 % faster at N = 4096
  * because the panel kernel already overlaps the product on a second stream) as per-chunk panel / product / finalize /
  * merge kernels.  Outputs are bit-identical either way.
- * `group` = candidate tiles per work group of the fused kernel, 0 = automatic.  Replaces point_selector.py:81,90-98,204-207. */
+ * `group` = candidate tiles that share L2 (work group of the fused kernel, CTA ordering of the separate tri-GEMM), 0 = automatic
+ * (~32 MB of panel digits; measured 8 … 64 at N = 4096: no setting beats it, tools/group_probe.py).  Replaces point_selector.py:81,90-98,204-207. */
 int bogp_set_fused(bogp_ctx* ctx, int enable, int group);
 int bogp_get_fused(const bogp_ctx* ctx);
 /* Screened sweeps of ONE SHARD of a sharded arg-max (select_parameters.py:282-294 spread over several GPUs): with enable = 1
